@@ -1,0 +1,148 @@
+/* mic_b200 — C-ABI of the B200-native captioning hot path.
+ *
+ * The reference (gchhablani/multilingual-image-captioning) has NO native/FFI boundary of its own: the
+ * arithmetic is emitted by XLA from flax.linen modules.  Each entry point below therefore names the
+ * reference site (file:line under /root/reference) or the upstream module (HF-PT twin under
+ * transformers/models/...) whose computation it replaces; SURVEY.md §8(a) row ids in brackets.
+ *
+ * Conventions (valid for XLA-FFI custom-call handlers and CUDA-graph capture):
+ *   - plain pointers + sizes, all pointers are DEVICE pointers unless noted; `stream` is a cudaStream_t
+ *   - every function only ENQUEUES work on `stream`: no allocation, no synchronisation, no default stream
+ *   - returns 0 on success, non-zero on error; mic_last_error() gives a thread-local message
+ *   - bf16 = __nv_bfloat16 bits; activations are row-major [rows, features]; Dense kernels are Flax
+ *     layout (in, out); LayerNorm/bias/stat vectors are fp32
+ */
+#ifndef MIC_B200_H_
+#define MIC_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIC_B200_ABI_VERSION 1
+
+#define MIC_ACT_NONE 0
+#define MIC_ACT_GELU 1       /* exact erf gelu: FlaxMBartDecoderLayer / ViT MLP */
+#define MIC_ACT_QUICK_GELU 2 /* x*sigmoid(1.702x): FlaxCLIPMLP */
+
+const char* mic_last_error(void);
+int mic_abi_version(void);
+
+/* ---- dense contraction ------------------------------------------------------------------------
+ * D[M,N] = act(A[M,K] * B[N,K]^T + bias) + residual        (tcgen05/TMEM, TMA-fed, bf16 in, fp32 acc)
+ * a_mn_major / b_mn_major = 0: operand stored [rows, K] (K contiguous); 1: stored [K, rows].
+ * Replaces every flax.linen.Dense / Conv on the path: FlaxCLIPAttention / FlaxCLIPMLP [E3,E4],
+ * visual_projection modeling_clip_vision_mbart.py:53-59,90 [E6], FlaxMBartAttention / FFN [D2-D4],
+ * patch conv as GEMM [E1], and all their dgrad / wgrad contractions under jax.value_and_grad
+ * main.py:696 [L2].  D is bf16 (d_is_f32=0) or fp32; accumulate=1 adds into an fp32 D.
+ * D2 (optional, bf16, ld = ldd) receives the pre-activation.  block_n/group_m = 0 -> auto. */
+int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
+                  long long ldb, int M, int N, int K, void* D, long long ldd, int d_is_f32, int accumulate,
+                  const float* bias, int act, void* D2, const void* residual, long long ldr, int block_n,
+                  int group_m);
+
+/* ---- tied lm_head fused with log-softmax / label-smoothed CE ------------------------------------
+ * modeling_clip_vision_mbart.py:170-178 [H1] + loss_fn main.py:658-680 [L1]; fp32 logits never reach HBM.
+ * stats: per row and per 128-column slab: max, sum exp(z-max), sum z; and z[label].
+ * Partial arrays are [mic_lm_head_num_partials(V), M]. */
+int mic_lm_head_num_partials(int vocab);
+int mic_lm_head_ce_stats(void* stream, const void* H, long long ldh, const void* E, long long lde,
+                         const float* bias, const int* labels, int M, int V, int K, float* pmax, float* psum,
+                         float* psumz, float* zlabel);
+/* finalize: lse[M], per-row loss, row_w = mask/sum(mask), out[0] = loss, out[1] = sum(mask) */
+int mic_ce_finalize(void* stream, const float* pmax, const float* psum, const float* psumz, const float* zlabel,
+                    const int* mask, int num_partials, int M, int V, float label_smoothing, float* lse,
+                    float* row_loss, float* row_w, float* out);
+/* backward [L2]: dlogits = (softmax - soft_labels) * row_w, bf16 [M, ldd], ldd % 256 == 0, pad cols = 0 */
+int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, const void* E, long long lde,
+                        const float* bias, const int* labels, const float* lse, const float* row_w, float conf,
+                        float low, int M, int V, int K, void* dlogits, long long ldd);
+/* decode-time lm_head for greedy / beam search [G4,G5]: per slab log-softmax partials + top-8 candidates */
+int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
+                       const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
+                       float* cand_val, int* cand_idx);
+
+/* ---- normalisation / embedding / elementwise (HBM-bound, vectorised, warp-shuffle reductions) ----
+ * flax.linen.LayerNorm (fp32 statistics, var = E[x^2]-E[x]^2) as used by FlaxCLIPEncoderLayer,
+ * pre_layrnorm, FlaxMBartDecoderLayer, layernorm_embedding, layer_norm [E2,E5,D5,D6]. x,y bf16 [M,d]. */
+int mic_layernorm_fwd(void* stream, const void* x, const float* gamma, const float* beta, float eps, void* y,
+                      float* mean, float* rstd, int M, int d);
+int mic_layernorm_bwd_num_partials(void);
+/* dx = dres + LN'(dy); dgamma/dbeta written (=). workspace: 2 * num_partials * d floats */
+int mic_layernorm_bwd(void* stream, const void* dy, const void* x, const float* gamma, const float* mean,
+                      const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, float* workspace,
+                      int M, int d);
+int mic_colsum_num_chunks(int M);
+/* dU = dY * act'(U) (bf16, skipped for MIC_ACT_NONE) and dbias (=|+=) column sums of the result.
+ * workspace: mic_colsum_num_chunks(M) * N floats.  Backward of Dense bias + ACT2FN [L2]. */
+int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act, void* dU,
+                       long long lddu, float* dbias, int accumulate, float* workspace, int M, int N);
+/* FlaxMBartDecoder embedding [D1]: shared[id]*scale + embed_positions[pos+offset] -> emb -> layernorm_embedding.
+ * pos_ids null -> position = row % pos_mod (arange(T), modeling_clip_vision_mbart.py:490-494). */
+int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids, int pos_mod, int pos_offset,
+                     const void* table, const void* pos_table, float scale, const float* gamma, const float* beta,
+                     float eps, void* emb, void* y, float* mean, float* rstd, int M, int d);
+/* backward of the lookup: d_table[id] += d_emb*scale (fp32 atomics onto the tied embedding gradient);
+ * d_pos_rows[t] (=) sum_b d_emb[b,t] */
+int mic_embed_bwd(void* stream, const int* ids, const void* d_emb, float scale, float* d_table, float* d_pos_rows,
+                  int B, int T, int d);
+int mic_batch_sum(void* stream, const void* x, int B, int T, int d, float* out, long long out_ld);
+/* FlaxCLIPVisionEmbeddings / ViT embeddings [E1,V1]: conv(stride=kernel=patch) == GEMM over patches.
+ * patchify: fp32 pixels (NHWC, or NCHW per modeling_vit_bart.py:445) -> bf16 [B*g*g, p*p*3] in (kh,kw,c)
+ * order; trunc_int reproduces the int32 cast of encode() modeling_clip_vision_mbart.py:330. */
+int mic_patchify(void* stream, const float* pixels, void* out, int B, int image_size, int patch, int channel_first,
+                 int trunc_int);
+int mic_vit_embed_ln_fwd(void* stream, const void* patch_out, const float* patch_bias, const void* cls,
+                         const void* pos, const float* gamma, const float* beta, float eps, int use_ln, void* emb,
+                         void* y, float* mean, float* rstd, int B, int S, int d);
+int mic_drop_cls_rows(void* stream, const void* d_emb, void* out, int B, int S, int d);
+/* optax.adamw main.py:629-635 + TrainState.apply_gradients :701 [O1]; flat fp32 p/m/v/g, bf16 shadow.
+ * hyper_dev (device, 8 floats): lr, b1, b2, eps, weight_decay, 1/(1-b1^t), 1/(1-b2^t), grad_scale */
+int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* shadow_bf16, const float* hyper_dev,
+              long long n);
+int mic_cast_f32_to_bf16(void* stream, const float* in, void* out, long long n);
+
+/* ---- attention ------------------------------------------------------------------------------------
+ * FlaxCLIPAttention / FlaxMBartAttention core [E3,D2,D3]: softmax((q/sqrt(hd)) k^T + mask) v for one
+ * (batch, head) per CTA; Tq,Tk <= 64, head_dim 64.  Q/K/V/O are strided views [B*T, ld] with head h at
+ * column h*64.  key_mask: int [B,Tk] (1 = keep) or null; causal: key j <= query i. lse: [B,H,Tq]. */
+int mic_attention_fwd(void* stream, const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                      long long ldv, void* O, long long ldo, float* lse, const int* key_mask, int causal, int B,
+                      int H, int Tq, int Tk, int head_dim, float scale);
+int mic_attention_bwd(void* stream, const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                      long long ldv, const void* O, long long ldo, const void* dO, long long lddo, const float* lse,
+                      const int* key_mask, int causal, void* dQ, long long lddq, void* dK, long long lddk, void* dV,
+                      long long lddv, int B, int H, int Tq, int Tk, int head_dim, float scale);
+/* cached 1-token attention of decode() modeling_clip_vision_mbart.py:519-651 [G4].  Cache element
+ * (row,pos,h,d) at ((row*cache_len+pos)*ldkv + h*64 + d).  ancestors [R,cache_len]: cache row holding
+ * position j of row r's beam history (replaces the cache gather of generation_...:945-953); null ->
+ * kv row = r / rows_per_kv (cross-attention over the image's visual tokens). */
+int mic_decode_attention(void* stream, const void* q, long long ldq, const void* k_cache, const void* v_cache,
+                         long long ldkv, const int* ancestors, int cache_len, int n_keys, int rows_per_kv, void* o,
+                         long long ldo, int R, int H, int head_dim, float scale);
+
+/* ---- search steps (generation_clip_vision_utils.py) ---------------------------------------------------
+ * merge the lm_head_search slab partials: per row log-softmax normaliser + top-8 (log-prob, token) */
+int mic_search_merge(void* stream, const float* pmax, const float* psum, const float* cand_val, const int* cand_idx,
+                     int num_partials, int R, float* row_lp, int* row_tok, float* row_max_logsum);
+/* beam_search_body_fn :822-966 steps 2-8 [G5]; forced_token >= 0 applies ForcedBOS/ForcedEOS [G2] */
+int mic_beam_step(void* stream, const float* row_lp, const int* row_tok, int forced_token, int B, int K, int L,
+                  int V, int cur_len, int eos_token_id, int early_stopping, float length_penalty, int* running_seq,
+                  float* running_scores, int* sequences, float* scores, int* finished, int* ancestors,
+                  int* next_token, int* active);
+/* beam_search_cond_fn :798-820 [G6] for the next iteration; writes *active */
+int mic_beam_cond(void* stream, const float* running_scores, const float* scores, const int* finished, int B, int K,
+                  int cur_len, int max_length, float length_penalty, int early_stopping, int* active);
+/* epilogue :978-990 */
+int mic_beam_finalize(void* stream, const int* sequences, const float* scores, const int* finished,
+                      const int* running_seq, const float* running_scores, int B, int K, int L, int* out_seq,
+                      float* out_scores);
+/* greedy_search_body_fn :489-522 / cond :480-487 [G7] */
+int mic_greedy_step(void* stream, const int* row_tok, int forced_token, int R, int L, int cur_len, int eos, int pad,
+                    int* sequences, int* finished, int* next_token, int* active);
+int mic_greedy_cond(void* stream, const int* finished, int R, int cur_len, int max_length, int* active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIC_B200_H_ */

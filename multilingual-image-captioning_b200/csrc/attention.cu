@@ -1,0 +1,504 @@
+// Attention for the tiny sequence lengths of the captioning path (50 visual tokens, 64 text tokens,
+// head_dim 64): one CTA per (batch, head) keeps the whole Q/K/V tile of that head in shared memory.
+// S=QK^T, softmax and PV run on warp-level bf16 MMA (m16n8k16) with fp32 accumulation; these
+// 64x64x64 problems are latency-bound, far too small to amortise a TMEM round trip, so the legacy
+// tensor path is the right tool here (they are ~1.3% of the step's FLOPs).
+//
+// Semantics = flax dot_product_attention_weights as used by FlaxCLIPAttention / FlaxMBartAttention:
+// scores = (q/sqrt(64)) . k ; additive mask 0/-inf from (causal AND key padding) ; softmax ; . v
+#include "common.cuh"
+
+#include "../../include/mic_b200.h"
+
+namespace {
+
+constexpr int HD = 64;     // head dim
+constexpr int TMAX = 64;   // max queries / keys per (batch, head) tile
+constexpr int LDS = 72;    // smem row pitch in bf16 (144 B: conflict-free fragment loads)
+
+__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// A fragment (16x16) from row-major smem tile S[m][k]
+__device__ __forceinline__ void frag_a(const bf16* s, int r0, int k0, int lane, uint32_t* a) {
+  const int g = lane >> 2, t = lane & 3;
+  a[0] = *reinterpret_cast<const uint32_t*>(s + (r0 + g) * LDS + k0 + 2 * t);
+  a[1] = *reinterpret_cast<const uint32_t*>(s + (r0 + g + 8) * LDS + k0 + 2 * t);
+  a[2] = *reinterpret_cast<const uint32_t*>(s + (r0 + g) * LDS + k0 + 2 * t + 8);
+  a[3] = *reinterpret_cast<const uint32_t*>(s + (r0 + g + 8) * LDS + k0 + 2 * t + 8);
+}
+// B fragment (16x8, "col") from smem tile stored as Bs[n][k] (k contiguous)
+__device__ __forceinline__ void frag_b(const bf16* s, int n0, int k0, int lane, uint32_t* b) {
+  const int g = lane >> 2, t = lane & 3;
+  b[0] = *reinterpret_cast<const uint32_t*>(s + (n0 + g) * LDS + k0 + 2 * t);
+  b[1] = *reinterpret_cast<const uint32_t*>(s + (n0 + g) * LDS + k0 + 2 * t + 8);
+}
+
+struct AttnArgs {
+  const bf16 *Q, *K, *V;
+  long long ldq, ldk, ldv;
+  bf16* O;
+  long long ldo;
+  float* lse;            // [B, H, Tq]
+  const int* key_mask;   // [B, Tk] (1 = keep) or null
+  int causal, B, H, Tq, Tk;
+  float scale;
+  // backward only
+  const bf16* dO;
+  long long lddo;
+  bf16 *dQ, *dK, *dV;
+  long long lddq, lddk, lddv;
+};
+
+// load a [rows x 64] head slice into smem (zero-filled beyond `rows`); optionally also its transpose
+__device__ __forceinline__ void load_tile(const bf16* g, long long ld, int rows, bf16* s, bf16* st, int tid, int nthreads) {
+  for (int i = tid; i < TMAX * (HD / 8); i += nthreads) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r < rows) u = *reinterpret_cast<const uint4*>(g + (long long)r * ld + c);
+    if (s) *reinterpret_cast<uint4*>(s + r * LDS + c) = u;
+    if (st) {
+      const bf16* e = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st[(c + j) * LDS + r] = e[j];
+    }
+  }
+}
+
+__device__ __forceinline__ bool key_allowed(int row, int col, int Tk, int causal, const int* km) {
+  if (col >= Tk) return false;
+  if (causal && col > row) return false;
+  if (km && km[col] == 0) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnArgs a) {
+  __shared__ __align__(16) bf16 sQ[TMAX * LDS];
+  __shared__ __align__(16) bf16 sK[TMAX * LDS];
+  __shared__ __align__(16) bf16 sVt[TMAX * LDS];
+  __shared__ int sMask[TMAX];
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_tile(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, a.Tq, sQ, nullptr, tid, 128);
+  load_tile(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, a.Tk, sK, nullptr, tid, 128);
+  load_tile(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, a.Tk, nullptr, sVt, tid, 128);
+  if (tid < TMAX) sMask[tid] = (a.key_mask && tid < a.Tk) ? a.key_mask[(long long)b * a.Tk + tid] : 1;
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (r0 >= a.Tq) return;
+  const int g = lane >> 2, t = lane & 3;
+  float s[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t af[4];
+    frag_a(sQ, r0, kk * 16, lane, af);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      uint32_t bfr[2];
+      frag_b(sK, nt * 8, kk * 16, lane, bfr);
+      mma_bf16_16816(s[nt], af, bfr);
+    }
+  }
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = r0 + g + (j >> 1) * 8, col = nt * 8 + 2 * t + (j & 1);
+      const bool ok = key_allowed(row, col, a.Tk, a.causal, a.key_mask ? sMask : nullptr);
+      s[nt][j] = ok ? s[nt][j] * a.scale : -INFINITY;
+      mx[j >> 1] = fmaxf(mx[j >> 1], s[nt][j]);
+    }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    if (mx[i] == -INFINITY) mx[i] = 0.f;
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = __expf(s[nt][j] - mx[j >> 1]);
+      s[nt][j] = p;
+      sum[j >> 1] += p;
+    }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[nd][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t af[4];
+    af[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    af[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    af[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    af[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      uint32_t bfr[2];
+      frag_b(sVt, nd * 8, kk * 16, lane, bfr);
+      mma_bf16_16816(o[nd], af, bfr);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = r0 + g + i * 8;
+    if (row < a.Tq) {
+      const float inv = sum[i] > 0.f ? 1.0f / sum[i] : 0.f;
+      bf16* orow = a.O + ((long long)b * a.Tq + row) * a.ldo + h * HD;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        *reinterpret_cast<uint32_t*>(orow + nd * 8 + 2 * t) = pack_bf16(o[nd][2 * i] * inv, o[nd][2 * i + 1] * inv);
+      if (a.lse && t == 0) a.lse[((long long)b * a.H + h) * a.Tq + row] = mx[i] + logf(sum[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: recompute P from Q,K and the saved log-sum-exp; dV = P^T dO ; dP = dO V^T ;
+// dS = scale * P o (dP - rowsum(dO o O)) ; dQ = dS K ; dK = dS^T Q
+// ---------------------------------------------------------------------------------------------
+constexpr int BWD_SMEM = (9 * TMAX * LDS) * 2 + TMAX * 4 * 2;
+
+__global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sQt = sQ + TMAX * LDS;
+  bf16* sK = sQt + TMAX * LDS;
+  bf16* sKt = sK + TMAX * LDS;
+  bf16* sV = sKt + TMAX * LDS;
+  bf16* sdO = sV + TMAX * LDS;
+  bf16* sdOt = sdO + TMAX * LDS;
+  bf16* sPt = sdOt + TMAX * LDS;
+  bf16* sdSt = sPt + TMAX * LDS;
+  float* sD = reinterpret_cast<float*>(sdSt + TMAX * LDS);
+  int* sMask = reinterpret_cast<int*>(sD + TMAX);
+
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bf16* gQ = a.Q + ((long long)b * a.Tq) * a.ldq + h * HD;
+  const bf16* gdO = a.dO + ((long long)b * a.Tq) * a.lddo + h * HD;
+  const bf16* gO = a.O + ((long long)b * a.Tq) * a.ldo + h * HD;
+  load_tile(gQ, a.ldq, a.Tq, sQ, sQt, tid, 128);
+  load_tile(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, a.Tk, sK, sKt, tid, 128);
+  load_tile(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, a.Tk, sV, nullptr, tid, 128);
+  load_tile(gdO, a.lddo, a.Tq, sdO, sdOt, tid, 128);
+  if (tid < TMAX) sMask[tid] = (a.key_mask && tid < a.Tk) ? a.key_mask[(long long)b * a.Tk + tid] : 1;
+  if (tid < TMAX) {
+    float d = 0.f;
+    if (tid < a.Tq) {
+      for (int c = 0; c < HD; c += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(gdO + (long long)tid * a.lddo + c);
+        const uint4 w = *reinterpret_cast<const uint4*>(gO + (long long)tid * a.ldo + c);
+        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+        const uint32_t* ww = reinterpret_cast<const uint32_t*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16(uu[j]), y = unpack_bf16(ww[j]);
+          d += x.x * y.x + x.y * y.y;
+        }
+      }
+    }
+    sD[tid] = d;
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  const int g = lane >> 2, t = lane & 3;
+  {
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[nt][j] = 0.f;
+        dp[nt][j] = 0.f;
+      }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t aq[4], ado[4];
+      frag_a(sQ, r0, kk * 16, lane, aq);
+      frag_a(sdO, r0, kk * 16, lane, ado);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t bk[2], bv[2];
+        frag_b(sK, nt * 8, kk * 16, lane, bk);
+        frag_b(sV, nt * 8, kk * 16, lane, bv);
+        mma_bf16_16816(s[nt], aq, bk);
+        mma_bf16_16816(dp[nt], ado, bv);
+      }
+    }
+    float lse[2], dd[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = r0 + g + i * 8;
+      lse[i] = row < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + row] : 0.f;
+      dd[i] = sD[row];
+    }
+    // P and dS (in place: s <- P, dp <- dS), stash transposes for the key-side contractions
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = j >> 1;
+        const int row = r0 + g + i * 8, col = nt * 8 + 2 * t + (j & 1);
+        const bool ok = row < a.Tq && key_allowed(row, col, a.Tk, a.causal, a.key_mask ? sMask : nullptr);
+        const float p = ok ? __expf(s[nt][j] * a.scale - lse[i]) : 0.f;
+        const float ds = p * (dp[nt][j] - dd[i]) * a.scale;
+        s[nt][j] = p;
+        dp[nt][j] = ds;
+        sPt[col * LDS + row] = __float2bfloat16_rn(p);
+        sdSt[col * LDS + row] = __float2bfloat16_rn(ds);
+      }
+    // dQ = dS K
+    float dq[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dq[nd][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t af[4];
+      af[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+      af[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+      af[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      af[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        uint32_t bfr[2];
+        frag_b(sKt, nd * 8, kk * 16, lane, bfr);
+        mma_bf16_16816(dq[nd], af, bfr);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = r0 + g + i * 8;
+      if (row < a.Tq) {
+        bf16* drow = a.dQ + ((long long)b * a.Tq + row) * a.lddq + h * HD;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd)
+          *reinterpret_cast<uint32_t*>(drow + nd * 8 + 2 * t) = pack_bf16(dq[nd][2 * i], dq[nd][2 * i + 1]);
+      }
+    }
+  }
+  __syncthreads();
+  // key side: this warp owns keys [r0, r0+16)
+  if (r0 < a.Tk) {
+    float dv[8][4], dk[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dv[nd][j] = 0.f;
+        dk[nd][j] = 0.f;
+      }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      uint32_t ap[4], ads[4];
+      frag_a(sPt, r0, qq * 16, lane, ap);
+      frag_a(sdSt, r0, qq * 16, lane, ads);
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        uint32_t bdo[2], bq[2];
+        frag_b(sdOt, nd * 8, qq * 16, lane, bdo);
+        frag_b(sQt, nd * 8, qq * 16, lane, bq);
+        mma_bf16_16816(dv[nd], ap, bdo);
+        mma_bf16_16816(dk[nd], ads, bq);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int key = r0 + g + i * 8;
+      if (key < a.Tk) {
+        bf16* krow = a.dK + ((long long)b * a.Tk + key) * a.lddk + h * HD;
+        bf16* vrow = a.dV + ((long long)b * a.Tk + key) * a.lddv + h * HD;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+          *reinterpret_cast<uint32_t*>(krow + nd * 8 + 2 * t) = pack_bf16(dk[nd][2 * i], dk[nd][2 * i + 1]);
+          *reinterpret_cast<uint32_t*>(vrow + nd * 8 + 2 * t) = pack_bf16(dv[nd][2 * i], dv[nd][2 * i + 1]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cached decode attention (1 query token per row), SURVEY.md A.3.
+// Self-attention reads the K/V history of a beam through an ancestor table instead of physically
+// reordering the cache (generation_clip_vision_utils.py:945-953 gathers 24 arrays every step):
+//   slot(r, j) = anc[r*T + j]  = cache row that holds position j of beam-row r's history
+// Cross-attention: K/V of the S visual tokens, shared by the beams of an image (row r -> r / beams).
+// One warp per (row, head); lanes split keys for the scores and head-dim for the output.
+// ---------------------------------------------------------------------------------------------
+struct DecAttnArgs {
+  const bf16* q;         // [R, ldq] (head h at h*64)
+  long long ldq;
+  const bf16 *kc, *vc;   // cache base: element (row, pos, h, d) at ((row*T + pos) * ldkv + h*64 + d)
+  long long ldkv;
+  const int* anc;        // [R, T] ancestor rows or null (identity)
+  int T;                 // cache length (positions per row)
+  int n_keys;            // keys to attend (cur position + 1) or S for cross
+  int rows_per_kv;       // cross-attention: beams per image (kv row = r / rows_per_kv); 1 otherwise
+  bf16* o;               // [R, ldo]
+  long long ldo;
+  int R, H;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wid >= a.R * a.H) return;
+  const int r = wid / a.H, h = wid % a.H;
+  // q in registers: every lane holds the full 64-d query (as fp32 pairs)
+  float qv[HD];
+  {
+    const bf16* qp = a.q + (long long)r * a.ldq + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(qp + c);
+      const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(uu[j]);
+        qv[c + 2 * j] = f.x * a.scale;
+        qv[c + 2 * j + 1] = f.y * a.scale;
+      }
+    }
+  }
+  const int kvrow_default = r / a.rows_per_kv;
+  float mx = -INFINITY;
+  float sc[4];   // up to 128 keys
+  const int nk = a.n_keys;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = lane + i * 32;
+    float s = -INFINITY;
+    if (j < nk) {
+      const int row = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
+      const bf16* kp = a.kc + ((long long)row * a.T + j) * a.ldkv + h * HD;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(kp + c);
+        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 f = unpack_bf16(uu[jj]);
+          acc += qv[c + 2 * jj] * f.x + qv[c + 2 * jj + 1] * f.y;
+        }
+      }
+      s = acc;
+    }
+    sc[i] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sc[i] = (lane + i * 32 < nk) ? __expf(sc[i] - mx) : 0.f;
+    sum += sc[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  // output: lane owns dims 2*lane, 2*lane+1 ; loop keys, broadcast p via shuffle
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = i * 32 + jj;
+      if (j >= nk) break;   // warp-uniform
+      const float p = __shfl_sync(0xffffffffu, sc[i], jj);
+      const int row = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
+      const bf16* vp = a.vc + ((long long)row * a.T + j) * a.ldkv + h * HD;
+      const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(vp + 2 * lane));
+      o0 += p * f.x;
+      o1 += p * f.y;
+    }
+  }
+  *reinterpret_cast<uint32_t*>(a.o + (long long)r * a.ldo + h * HD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+}
+
+}  // namespace
+
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+static int check_attn(int head_dim, int Tq, int Tk) {
+  MIC_CHECK_ARG(head_dim == HD, "attention: head_dim %d != 64", head_dim);
+  MIC_CHECK_ARG(Tq >= 1 && Tq <= TMAX && Tk >= 1 && Tk <= TMAX, "attention: Tq=%d Tk=%d must be in [1,64]", Tq, Tk);
+  return MIC_OK;
+}
+
+extern "C" int mic_attention_fwd(void* stream, const void* Q, long long ldq, const void* K, long long ldk,
+                                 const void* V, long long ldv, void* O, long long ldo, float* lse,
+                                 const int* key_mask, int causal, int B, int H, int Tq, int Tk, int head_dim,
+                                 float scale) {
+  int rc = check_attn(head_dim, Tq, Tk);
+  if (rc) return rc;
+  AttnArgs a = {};
+  a.Q = (const bf16*)Q; a.K = (const bf16*)K; a.V = (const bf16*)V;
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
+  a.O = (bf16*)O; a.ldo = ldo; a.lse = lse; a.key_mask = key_mask;
+  a.causal = causal; a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.scale = scale;
+  attention_fwd_kernel<<<B * H, 128, 0, STREAM>>>(a);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_attention_bwd(void* stream, const void* Q, long long ldq, const void* K, long long ldk,
+                                 const void* V, long long ldv, const void* O, long long ldo, const void* dO,
+                                 long long lddo, const float* lse, const int* key_mask, int causal, void* dQ,
+                                 long long lddq, void* dK, long long lddk, void* dV, long long lddv, int B, int H,
+                                 int Tq, int Tk, int head_dim, float scale) {
+  int rc = check_attn(head_dim, Tq, Tk);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    MIC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr = true;
+  }
+  AttnArgs a = {};
+  a.Q = (const bf16*)Q; a.K = (const bf16*)K; a.V = (const bf16*)V;
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
+  a.O = (bf16*)const_cast<void*>(O); a.ldo = ldo; a.lse = const_cast<float*>(lse); a.key_mask = key_mask;
+  a.causal = causal; a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.scale = scale;
+  a.dO = (const bf16*)dO; a.lddo = lddo;
+  a.dQ = (bf16*)dQ; a.dK = (bf16*)dK; a.dV = (bf16*)dV;
+  a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
+  attention_bwd_kernel<<<B * H, 128, BWD_SMEM, STREAM>>>(a);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_decode_attention(void* stream, const void* q, long long ldq, const void* k_cache,
+                                    const void* v_cache, long long ldkv, const int* ancestors, int cache_len,
+                                    int n_keys, int rows_per_kv, void* o, long long ldo, int R, int H, int head_dim,
+                                    float scale) {
+  MIC_CHECK_ARG(head_dim == HD, "decode attention: head_dim %d != 64", head_dim);
+  MIC_CHECK_ARG(n_keys >= 1 && n_keys <= 128 && n_keys <= cache_len, "decode attention: n_keys=%d cache_len=%d",
+                n_keys, cache_len);
+  DecAttnArgs a;
+  a.q = (const bf16*)q; a.ldq = ldq; a.kc = (const bf16*)k_cache; a.vc = (const bf16*)v_cache; a.ldkv = ldkv;
+  a.anc = ancestors; a.T = cache_len; a.n_keys = n_keys; a.rows_per_kv = rows_per_kv < 1 ? 1 : rows_per_kv;
+  a.o = (bf16*)o; a.ldo = ldo; a.R = R; a.H = H; a.scale = scale;
+  decode_attention_kernel<<<(R * H + 3) / 4, 128, 0, STREAM>>>(a);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}

@@ -1,0 +1,676 @@
+// HBM-bound kernels of the captioning path: LayerNorm fwd/bwd, embedding gather/scatter, patchify,
+// activation backward + bias-gradient column sums, CE finalisation, AdamW.  All use 16-byte vector
+// access on the contiguous feature dimension and warp-shuffle reductions; fp32 statistics.
+#include "common.cuh"
+
+#include "../../include/mic_b200.h"
+
+namespace {
+
+constexpr int LN_MAX_ITERS = 4;   // features <= 1024 (32 lanes * 8 elements * 4)
+
+__device__ __forceinline__ void load8(const bf16* p, float* x) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
+  f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
+  f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
+  f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float* x) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                            pack_bf16(x[6], x[7]));
+}
+__device__ __forceinline__ void load8f(const float* p, float* x) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+
+// flax.linen.LayerNorm statistics: mean, E[x^2] - mean^2 (clamped at 0), biased
+__device__ __forceinline__ void ln_stats(const float (*x)[8], int d, int lane, float* mean, float* rstd, float eps) {
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    if (lane * 8 + it * 256 < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += x[it][j];
+        s2 += x[it][j] * x[it][j];
+      }
+    }
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float m = s / d;
+  const float var = fmaxf(s2 / d - m * m, 0.f);
+  *mean = m;
+  *rstd = rsqrtf(var + eps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward.  One warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            bf16* __restrict__ y, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float v[LN_MAX_ITERS][8];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) load8(x + (long long)row * d + c, v[it]);
+  }
+  float mean, rstd;
+  ln_stats(v, d, lane, &mean, &rstd, eps);
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + b[j];
+      store8(y + (long long)row * d + c, o);
+    }
+  }
+  if (lane == 0 && mean_out) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward.  Persistent blocks stride over rows; per-thread dgamma/dbeta partials are
+// reduced across the block's warps in shared memory and written to partial[block][d].
+//   dx = dres + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))
+// ---------------------------------------------------------------------------------------------
+constexpr int LNB_WARPS = 8;
+__global__ void __launch_bounds__(LNB_WARPS * 32)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
+                     bf16* __restrict__ dx, float* __restrict__ part_dg, float* __restrict__ part_db, int M, int d) {
+  __shared__ float red[LNB_WARPS][1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float dg[LN_MAX_ITERS][8], db[LN_MAX_ITERS][8], g[LN_MAX_ITERS][8];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dg[it][j] = 0.f;
+      db[it][j] = 0.f;
+      g[it][j] = 0.f;
+    }
+    if (c < d) load8f(gamma + c, g[it]);
+  }
+  for (int row = blockIdx.x * LNB_WARPS + warp; row < M; row += gridDim.x * LNB_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float dyv[LN_MAX_ITERS][8], xh[LN_MAX_ITERS][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      const int c = lane * 8 + it * 256;
+      if (c < d) {
+        load8(dy + (long long)row * d + c, dyv[it]);
+        load8(x + (long long)row * d + c, xh[it]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[it][j] = (xh[it][j] - mu) * rs;
+          const float t = dyv[it][j] * g[it][j];
+          s1 += t;
+          s2 += t * xh[it][j];
+          dg[it][j] += dyv[it][j] * xh[it][j];
+          db[it][j] += dyv[it][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      const int c = lane * 8 + it * 256;
+      if (c < d) {
+        float o[8], r[8];
+        if (dres) load8(dres + (long long)row * d + c, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rs * (dyv[it][j] * g[it][j] - s1 - xh[it][j] * s2);
+          if (dres) o[j] += r[j];
+        }
+        store8(dx + (long long)row * d + c, o);
+      }
+    }
+  }
+  // block reduce dgamma then dbeta
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      const int c = lane * 8 + it * 256;
+      if (c < d) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][c + j] = pass == 0 ? dg[it][j] : db[it][j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < LNB_WARPS; ++w) s += red[w][c];
+      (pass == 0 ? part_dg : part_db)[(long long)blockIdx.x * d + c] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// out[c] (=|+=) sum_p part[p][c]
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out,
+                                       int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(long long)p * n + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dU = dY * act'(U)  (optional) and column sums of the result (bias gradient), two-stage.
+// block = 32 column-groups (8 cols each) x 8 row lanes; grid = (ceil(N/256), row_chunks)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __restrict__ U, long long ldu, int act,
+                      bf16* __restrict__ dU, long long lddu, float* __restrict__ part, int M, int N,
+                      int rows_per_chunk) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float g[8];
+      load8(dY + (long long)r * ldy + c, g);
+      if (act != MIC_ACT_NONE) {
+        float u[8];
+        load8(U + (long long)r * ldu + c, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = bf16_round(g[j] * act_bwd(u[j], act));
+        store8(dU + (long long)r * lddu + c, g);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (part && blockIdx.x * 256 + t < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][t];
+    part[(long long)blockIdx.y * N + blockIdx.x * 256 + t] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder embedding: shared[id]*scale + positions[pos+offset] -> emb (bf16) -> LayerNorm -> y
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_ln_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, int pos_mod, int pos_offset,
+                    const bf16* __restrict__ table, const bf16* __restrict__ pos_table, float scale,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, bf16* __restrict__ emb,
+                    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const long long id = ids[row];
+  const long long pos = (pos_ids ? pos_ids[row] : (row % pos_mod)) + pos_offset;
+  float v[LN_MAX_ITERS][8];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float e[8], p[8];
+      load8(table + id * d + c, e);
+      load8(pos_table + pos * d + c, p);
+      // Flax bf16 mode rounds (embedding*scale) and the sum to bf16; we keep one rounding at the store
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[it][j] = bf16_round(e[j] * scale + p[j]);
+      if (emb) store8(emb + (long long)row * d + c, v[it]);
+    }
+  }
+  float mean, rstd;
+  ln_stats(v, d, lane, &mean, &rstd, eps);
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + b[j];
+      store8(y + (long long)row * d + c, o);
+    }
+  }
+  if (lane == 0 && mean_out) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// scatter-add of d_emb*scale into the (tied) embedding gradient, fp32 atomics. one warp per row.
+__global__ void __launch_bounds__(256)
+embed_scatter_bwd_kernel(const int* __restrict__ ids, const bf16* __restrict__ d_emb, float scale,
+                         float* __restrict__ d_table, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const long long id = ids[row];
+  for (int c = lane * 8; c < d; c += 256) {
+    float g[8];
+    load8(d_emb + (long long)row * d + c, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(d_table + id * d + c + j, g[j] * scale);
+  }
+}
+
+// out[t][c] = sum_b x[(b*T + t)][c]  (position-embedding gradient, class/position grads of the ViT)
+// grid = (T, ceil(d/256)); block 256 = 32 col groups... here 1 thread per column for simplicity
+__global__ void __launch_bounds__(256)
+batch_sum_kernel(const bf16* __restrict__ x, int B, int T, int d, float* __restrict__ out, long long out_ld) {
+  const int t = blockIdx.x;
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += __bfloat162float(x[((long long)b * T + t) * d + c]);
+  out[(long long)t * out_ld + c] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vision front end
+// ---------------------------------------------------------------------------------------------
+// pixels fp32 (NHWC or NCHW) -> bf16 patch matrix [B*g*g, p*p*3], k ordered (kh, kw, c) = HWIO kernel
+// rows.  trunc_int reproduces encode()'s int32 cast (modeling_clip_vision_mbart.py:330).
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ px, bf16* __restrict__ out, int B, int img, int p, int nchw, int trunc_int) {
+  const int g = img / p;
+  const int K = p * p * 3;
+  const long long total = (long long)B * g * g * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long m = i / K;
+    const int c = k % 3, kw = (k / 3) % p, kh = k / (3 * p);
+    const int pw = (int)(m % g), ph = (int)((m / g) % g);
+    const int b = (int)(m / (g * g));
+    const int yy = ph * p + kh, xx = pw * p + kw;
+    float v = nchw ? px[(((long long)b * 3 + c) * img + yy) * img + xx]
+                   : px[(((long long)b * img + yy) * img + xx) * 3 + c];
+    if (trunc_int) v = truncf(v);
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// tokens: [cls ; patch_out(+bias)] + pos -> emb (bf16) -> optional LayerNorm -> y.  One warp per token row.
+__global__ void __launch_bounds__(256)
+vit_embed_ln_fwd_kernel(const bf16* __restrict__ patch_out, const float* __restrict__ patch_bias,
+                        const bf16* __restrict__ cls, const bf16* __restrict__ pos, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, int use_ln, bf16* __restrict__ emb,
+                        bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int B, int S,
+                        int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B * S) return;
+  const int b = row / S, t = row % S;
+  float v[LN_MAX_ITERS][8];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float e[8], p[8];
+      if (t == 0) {
+        load8(cls + c, e);
+      } else {
+        load8(patch_out + ((long long)b * (S - 1) + (t - 1)) * d + c, e);
+        if (patch_bias) {
+          float pb[8];
+          load8f(patch_bias + c, pb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = bf16_round(e[j] + pb[j]);
+        }
+      }
+      load8(pos + (long long)t * d + c, p);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[it][j] = bf16_round(e[j] + p[j]);
+      if (emb) store8(emb + (long long)row * d + c, v[it]);
+    }
+  }
+  if (!use_ln) {
+#pragma unroll
+    for (int it = 0; it < LN_MAX_ITERS; ++it) {
+      const int c = lane * 8 + it * 256;
+      if (c < d) store8(y + (long long)row * d + c, v[it]);
+    }
+    return;
+  }
+  float mean, rstd;
+  ln_stats(v, d, lane, &mean, &rstd, eps);
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float g[8], bb[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, bb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + bb[j];
+      store8(y + (long long)row * d + c, o);
+    }
+  }
+  if (lane == 0 && mean_out) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// d_emb [B,S,d] -> compact d_patch_out [B*(S-1), d] (drop the class token row)
+__global__ void __launch_bounds__(256)
+drop_cls_rows_kernel(const bf16* __restrict__ d_emb, bf16* __restrict__ out, int B, int S, int d) {
+  const long long n8 = (long long)B * (S - 1) * d / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    const long long r = e / d;
+    const int c = (int)(e % d);
+    const long long b = r / (S - 1), t = r % (S - 1) + 1;
+    *reinterpret_cast<uint4*>(out + e) = *reinterpret_cast<const uint4*>(d_emb + ((b * S + t) * d + c));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CE finalisation: combine the per-slab partials -> lse, per-row loss, weights, scalar loss
+// one warp per row for the combine; then a single-block reduction for the scalar
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, const float* __restrict__ psumz,
+               const float* __restrict__ zlabel, int nparts, int M, int V, float eps_ls, float* __restrict__ lse_out,
+               float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float mx = -INFINITY;
+  for (int p = lane; p < nparts; p += 32) mx = fmaxf(mx, pmax[(long long)p * M + row]);
+  mx = warp_max(mx);
+  float s = 0.f, sz = 0.f;
+  for (int p = lane; p < nparts; p += 32) {
+    const float m = pmax[(long long)p * M + row];
+    if (m > -INFINITY) s += psum[(long long)p * M + row] * __expf(m - mx);
+    if (psumz) sz += psumz[(long long)p * M + row];
+  }
+  s = warp_sum(s);
+  sz = warp_sum(sz);
+  if (lane == 0) {
+    const float lse = mx + logf(s);
+    lse_out[row] = lse;
+    if (row_loss) {
+      // main.py:666-675 closed form: lse - conf*z_y - low*(sum z - z_y) - const
+      const float conf = 1.0f - eps_ls;
+      const float low = eps_ls / (float)(V - 1);
+      float cst = 0.f;
+      if (eps_ls > 0.f) cst = -(conf * logf(conf) + (float)(V - 1) * low * logf(low + 1e-20f));
+      const float zy = zlabel[row];
+      row_loss[row] = lse - conf * zy - low * (sz - zy) - cst;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ce_reduce_kernel(const float* __restrict__ row_loss, const int* __restrict__ mask, int M, float* __restrict__ row_w,
+                 float* __restrict__ out) {
+  __shared__ float sl[32], sc[32];
+  float l = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const float m = mask ? (float)mask[i] : 1.f;
+    l += row_loss[i] * m;
+    c += m;
+  }
+  l = warp_sum(l);
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) {
+    sl[threadIdx.x >> 5] = l;
+    sc[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    l = sl[threadIdx.x];
+    c = sc[threadIdx.x];
+    l = warp_sum(l);
+    c = warp_sum(c);
+    if (threadIdx.x == 0) {
+      sl[0] = l;
+      sc[0] = c;
+      out[0] = l / c;
+      out[1] = c;
+    }
+  }
+  __syncthreads();
+  const float inv = 1.0f / sc[0];
+  if (row_w)
+    for (int i = threadIdx.x; i < M; i += blockDim.x) row_w[i] = (mask ? (float)mask[i] : 1.f) * inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdamW (optax 0.0.9 chain: scale_by_adam -> add_decayed_weights -> scale(-lr)), flat fp32 state,
+// bf16 shadow refresh.  hp[] lives in device memory so a captured graph can be replayed:
+//   hp = {lr, b1, b2, eps, wd, 1/(1-b1^t), 1/(1-b2^t), grad_scale}
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+             bf16* __restrict__ shadow, const float* __restrict__ hp, long long n) {
+  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], c1 = hp[5], c2 = hp[6], gs = hp[7];
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = ga[j] * gs;
+      ma[j] = b1 * ma[j] + (1.f - b1) * gr;
+      va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
+      const float upd = (ma[j] * c1) / (sqrtf(va[j] * c2) + eps) + wd * pa[j];
+      pa[j] -= lr * upd;
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow)
+      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16(pa[0], pa[1]), pack_bf16(pa[2], pa[3]));
+  }
+  // tail (n not a multiple of 4)
+  const long long tail0 = n4 << 2;
+  const long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float gr = g[i] * gs;
+    const float mj = b1 * m[i] + (1.f - b1) * gr;
+    const float vj = b2 * v[i] + (1.f - b2) * gr * gr;
+    const float upd = (mj * c1) / (sqrtf(vj * c2) + eps) + wd * p[i];
+    const float pj = p[i] - lr * upd;
+    p[i] = pj;
+    m[i] = mj;
+    v[i] = vj;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pj);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+inline int grid_for(long long work_items, int per_block, int cap_mult = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)mic_num_sms() * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int mic_layernorm_fwd(void* stream, const void* x, const float* gamma, const float* beta, float eps,
+                                 void* y, float* mean, float* rstd, int M, int d) {
+  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm: d=%d must be a multiple of 8 and <= 1024", d);
+  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, M, d);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_layernorm_bwd_num_partials(void) { return mic_num_sms() * 2; }
+
+extern "C" int mic_layernorm_bwd(void* stream, const void* dy, const void* x, const float* gamma, const float* mean,
+                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 float* workspace, int M, int d) {
+  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm_bwd: d=%d must be a multiple of 8 and <= 1024", d);
+  int nb = mic_layernorm_bwd_num_partials();
+  const int need = (M + LNB_WARPS - 1) / LNB_WARPS;
+  if (nb > need) nb = need;
+  float* pg = workspace;
+  float* pb = workspace + (long long)nb * d;
+  layernorm_bwd_kernel<<<nb, LNB_WARPS * 32, 0, STREAM>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
+                                                          (const bf16*)dres, (bf16*)dx, pg, pb, M, d);
+  MIC_CHECK_LAUNCH();
+  reduce_partials_kernel<<<(d + 255) / 256, 256, 0, STREAM>>>(pg, nb, d, dgamma, 0);
+  reduce_partials_kernel<<<(d + 255) / 256, 256, 0, STREAM>>>(pb, nb, d, dbeta, 0);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_colsum_num_chunks(int M) {
+  int chunks = (M + 255) / 256;
+  if (chunks > 64) chunks = 64;
+  return chunks < 1 ? 1 : chunks;
+}
+
+extern "C" int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act,
+                                  void* dU, long long lddu, float* dbias, int accumulate, float* workspace, int M,
+                                  int N) {
+  MIC_CHECK_ARG(N % 8 == 0 && ldy % 8 == 0, "act_bwd_colsum: N and ld must be multiples of 8");
+  MIC_CHECK_ARG(act == MIC_ACT_NONE || (U && dU), "act_bwd_colsum: activation backward needs U and dU");
+  const int chunks = mic_colsum_num_chunks(M);
+  const int rows_per_chunk = (M + chunks - 1) / chunks;
+  dim3 grid((N + 255) / 256, chunks);
+  act_bwd_colsum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)dY, ldy, (const bf16*)U, ldu, act, (bf16*)dU, lddu,
+                                                  dbias ? workspace : nullptr, M, N, rows_per_chunk);
+  MIC_CHECK_LAUNCH();
+  if (dbias) {
+    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, STREAM>>>(workspace, chunks, N, dbias, accumulate);
+    MIC_CHECK_LAUNCH();
+  }
+  return MIC_OK;
+}
+
+extern "C" int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids, int pos_mod, int pos_offset,
+                                const void* table, const void* pos_table, float scale, const float* gamma,
+                                const float* beta, float eps, void* emb, void* y, float* mean, float* rstd, int M,
+                                int d) {
+  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024, "embed: d=%d must be a multiple of 8 and <= 1024", d);
+  embed_ln_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(ids, pos_ids, pos_mod, pos_offset, (const bf16*)table,
+                                                       (const bf16*)pos_table, scale, gamma, beta, eps, (bf16*)emb,
+                                                       (bf16*)y, mean, rstd, M, d);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_embed_bwd(void* stream, const int* ids, const void* d_emb, float scale, float* d_table,
+                             float* d_pos_rows, int B, int T, int d) {
+  const int M = B * T;
+  embed_scatter_bwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(ids, (const bf16*)d_emb, scale, d_table, M, d);
+  MIC_CHECK_LAUNCH();
+  if (d_pos_rows) {
+    dim3 grid(T, (d + 255) / 256);
+    batch_sum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)d_emb, B, T, d, d_pos_rows, d);
+    MIC_CHECK_LAUNCH();
+  }
+  return MIC_OK;
+}
+
+extern "C" int mic_batch_sum(void* stream, const void* x, int B, int T, int d, float* out, long long out_ld) {
+  dim3 grid(T, (d + 255) / 256);
+  batch_sum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)x, B, T, d, out, out_ld);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_patchify(void* stream, const float* pixels, void* out, int B, int image_size, int patch,
+                            int channel_first, int trunc_int) {
+  MIC_CHECK_ARG(image_size % patch == 0, "image size %d not divisible by patch %d", image_size, patch);
+  const long long total = (long long)B * image_size * image_size * 3;
+  patchify_kernel<<<grid_for(total, 256 * 4), 256, 0, STREAM>>>(pixels, (bf16*)out, B, image_size, patch,
+                                                                channel_first, trunc_int);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_vit_embed_ln_fwd(void* stream, const void* patch_out, const float* patch_bias, const void* cls,
+                                    const void* pos, const float* gamma, const float* beta, float eps, int use_ln,
+                                    void* emb, void* y, float* mean, float* rstd, int B, int S, int d) {
+  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024, "vit_embed: d=%d must be a multiple of 8 and <= 1024", d);
+  const int M = B * S;
+  vit_embed_ln_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>((const bf16*)patch_out, patch_bias, (const bf16*)cls,
+                                                           (const bf16*)pos, gamma, beta, eps, use_ln, (bf16*)emb,
+                                                           (bf16*)y, mean, rstd, B, S, d);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_drop_cls_rows(void* stream, const void* d_emb, void* out, int B, int S, int d) {
+  MIC_CHECK_ARG(d % 8 == 0, "drop_cls_rows: d must be a multiple of 8");
+  drop_cls_rows_kernel<<<grid_for((long long)B * (S - 1) * d / 8, 256), 256, 0, STREAM>>>((const bf16*)d_emb,
+                                                                                          (bf16*)out, B, S, d);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_ce_finalize(void* stream, const float* pmax, const float* psum, const float* psumz,
+                               const float* zlabel, const int* mask, int num_partials, int M, int V,
+                               float label_smoothing, float* lse, float* row_loss, float* row_w, float* out) {
+  ce_rows_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(pmax, psum, psumz, zlabel, num_partials, M, V, label_smoothing, lse,
+                                                  row_loss);
+  MIC_CHECK_LAUNCH();
+  if (row_loss && out) {
+    ce_reduce_kernel<<<1, 1024, 0, STREAM>>>(row_loss, mask, M, row_w, out);
+    MIC_CHECK_LAUNCH();
+  }
+  return MIC_OK;
+}
+
+extern "C" int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* shadow_bf16,
+                         const float* hyper_dev, long long n) {
+  MIC_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
+                    ((uintptr_t)g & 15) == 0,
+                "adamw: state pointers must be 16-byte aligned");
+  adamw_kernel<<<grid_for(n / 4 + 1, 256, 16), 256, 0, STREAM>>>(p, m, v, g, (bf16*)shadow_bf16, hyper_dev, n);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_cast_f32_to_bf16(void* stream, const float* in, void* out, long long n) {
+  cast_f32_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, STREAM>>>(in, (bf16*)out, n);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}

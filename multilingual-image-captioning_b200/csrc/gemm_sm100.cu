@@ -1,0 +1,219 @@
+// Host launchers (C-ABI) for the tcgen05 GEMM family.  See include/mic_b200.h for the contract.
+#include "gemm_sm100.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mic_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// error string / device info / tensor-map encode
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void mic_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* mic_last_error(void) { return g_err; }
+extern "C" int mic_abi_version(void) { return MIC_B200_ABI_VERSION; }
+
+int mic_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int mic_make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                          uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  MIC_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  MIC_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand pointer %p not 16-byte aligned", ptr);
+  MIC_CHECK_ARG(ld % 8 == 0, "TMA operand leading dimension %llu not a multiple of 8 elements",
+                (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MIC_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u",
+                (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner,
+                box_outer);
+  return MIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+using namespace micgemm;
+
+static int pick_block_n(int M, int N, int forced) {
+  if (forced == 128 || forced == 192 || forced == 256) return forced;
+  const int sms = mic_num_sms();
+  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  int best = 256;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long tiles = (long long)mb * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double cost = (double)waves * bn * (1.0 + 6.0 / bn);   // mild preference for wide tiles
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+struct Operands {
+  CUtensorMap ta, tb;
+  Shape shape;
+  int bn;
+};
+
+static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb,
+                          int M, int N, int K, int block_n, int group_m) {
+  MIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
+  o->bn = pick_block_n(M, N, block_n);
+  int rc;
+  if (!a_mn)
+    rc = mic_make_tmap_bf16_2d(&o->ta, A, K, M, lda, BLOCK_K, BLOCK_M);
+  else
+    rc = mic_make_tmap_bf16_2d(&o->ta, A, M, K, lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = mic_make_tmap_bf16_2d(&o->tb, B, K, N, ldb, BLOCK_K, o->bn);
+  else
+    rc = mic_make_tmap_bf16_2d(&o->tb, B, N, K, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  Shape& s = o->shape;
+  s.M = M;
+  s.N = N;
+  s.K = K;
+  s.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  s.num_n_blocks = (N + o->bn - 1) / o->bn;
+  if (group_m <= 0) group_m = ((long long)M * K * 2 <= (48ll << 20)) ? s.num_m_blocks : 16;
+  s.group_m = group_m < s.num_m_blocks ? group_m : s.num_m_blocks;
+  if (s.group_m < 1) s.group_m = 1;
+  return MIC_OK;
+}
+
+template <int A_MN, int B_MN, int BN, class Epi>
+static int launch_one(cudaStream_t stream, const Operands& o, const typename Epi::Params& ep) {
+  auto kern = gemm_kernel<A_MN, B_MN, BN, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks;
+  const int grid = tiles < mic_num_sms() ? tiles : mic_num_sms();
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.shape, ep);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+template <int A_MN, int B_MN, class Epi>
+static int launch_bn(cudaStream_t stream, const Operands& o, const typename Epi::Params& ep) {
+  switch (o.bn) {
+    case 256: return launch_one<A_MN, B_MN, 256, Epi>(stream, o, ep);
+    case 192: return launch_one<A_MN, B_MN, 192, Epi>(stream, o, ep);
+    default: return launch_one<A_MN, B_MN, 128, Epi>(stream, o, ep);
+  }
+}
+
+extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, long long lda,
+                             const void* B, long long ldb, int M, int N, int K, void* D, long long ldd, int d_is_f32,
+                             int accumulate, const float* bias, int act, void* D2, const void* residual,
+                             long long ldr, int block_n, int group_m) {
+  Operands o;
+  int rc = setup_operands(&o, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, block_n, group_m);
+  if (rc) return rc;
+  MIC_CHECK_ARG(D != nullptr, "null output");
+  MIC_CHECK_ARG(!(accumulate && !d_is_f32), "accumulate requires fp32 output");
+  EpiStoreParams ep;
+  ep.D = D;
+  ep.ldd = ldd;
+  ep.d_f32 = d_is_f32;
+  ep.accumulate = accumulate;
+  ep.bias = bias;
+  ep.act = act;
+  ep.D2 = reinterpret_cast<bf16*>(D2);
+  ep.residual = reinterpret_cast<const bf16*>(residual);
+  ep.ldr = ldr;
+  ep.out_scale = 1.0f;
+  const int esz = d_is_f32 ? 4 : 2;
+  bool vec = ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((ldd * esz) % 16 == 0);
+  if (bias) vec = vec && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  if (D2) vec = vec && ((reinterpret_cast<uintptr_t>(D2) & 15) == 0) && (ldd % 8 == 0);
+  if (residual) vec = vec && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) && (ldr % 8 == 0);
+  ep.vec_ok = vec ? 1 : 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!a_mn_major && b_mn_major) return launch_bn<0, 1, EpiStore>(s, o, ep);
+  if (!a_mn_major && !b_mn_major) return launch_bn<0, 0, EpiStore>(s, o, ep);
+  if (a_mn_major && b_mn_major) return launch_bn<1, 1, EpiStore>(s, o, ep);
+  mic_set_error("GEMM layout (A MN-major, B K-major) is not instantiated");
+  return MIC_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused lm_head + cross-entropy
+// ------------------------------------------------------------------------------------------------
+extern "C" int mic_lm_head_num_partials(int vocab) { return 2 * ((vocab + 255) / 256); }
+
+extern "C" int mic_lm_head_ce_stats(void* stream, const void* H, long long ldh, const void* E, long long lde,
+                                    const float* bias, const int* labels, int M, int V, int K, float* pmax,
+                                    float* psum, float* psumz, float* zlabel) {
+  Operands o;
+  int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, (M + BLOCK_M - 1) / BLOCK_M);
+  if (rc) return rc;
+  EpiCEStatsParams ep = {bias, labels, pmax, psum, psumz, zlabel};
+  return launch_one<0, 0, 256, EpiCEStats>(reinterpret_cast<cudaStream_t>(stream), o, ep);
+}
+
+extern "C" int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, const void* E, long long lde,
+                                   const float* bias, const int* labels, const float* lse, const float* row_w,
+                                   float conf, float low, int M, int V, int K, void* dlogits, long long ldd) {
+  MIC_CHECK_ARG(ldd % 256 == 0 && ldd >= V, "dlogits leading dimension %lld must be a multiple of 256 >= V", ldd);
+  Operands o;
+  int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, (M + BLOCK_M - 1) / BLOCK_M);
+  if (rc) return rc;
+  // cover the padded columns too so they are written as zeros
+  o.shape.num_n_blocks = (int)(ldd / 256);
+  EpiCEGradParams ep = {bias, labels, lse, row_w, conf, low, reinterpret_cast<bf16*>(dlogits), ldd};
+  return launch_one<0, 0, 256, EpiCEGrad>(reinterpret_cast<cudaStream_t>(stream), o, ep);
+}
+
+extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
+                                  const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
+                                  float* cand_val, int* cand_idx) {
+  Operands o;
+  int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, (M + BLOCK_M - 1) / BLOCK_M);
+  if (rc) return rc;
+  EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx};
+  return launch_one<0, 0, 256, EpiSearch>(reinterpret_cast<cudaStream_t>(stream), o, ep);
+}
