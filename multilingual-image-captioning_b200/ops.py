@@ -1,0 +1,231 @@
+"""Operator layer: torch tensors in, C-ABI calls out (include/mic_b200.h).
+
+torch is used only for device memory and the current CUDA stream; every function enqueues hand-written
+sm_100a kernels from libmic_b200.so.  Nothing here computes on the host and nothing falls back to
+torch math.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib, check
+
+ACT = {"none": 0, None: 0, "gelu": 1, "quick_gelu": 2}
+BF16 = torch.bfloat16
+F32 = torch.float32
+I32 = torch.int32
+
+LAUNCHES = [0]      # number of C-ABI kernel-launching calls (bench.py reports it)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    LAUNCHES[0] += 1
+    check(getattr(lib(), name)(_s(), *args), name)
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, f"need a row-major 2-D view, got {tuple(t.shape)} {t.stride()}"
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM family
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, act="none", pre_act_out=None,
+         residual=None, accumulate=False, block_n=0, group_m=0):
+    """D[M,N] = act(A[M,K] B[N,K]^T + bias) + residual.
+    a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True, Flax kernel)."""
+    assert a.dtype == BF16 and b.dtype == BF16
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N)
+    d_f32 = out.dtype == F32
+    if pre_act_out is not None:
+        assert pre_act_out.dtype == BF16 and _ld(pre_act_out) == _ld(out)
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() == N
+    _call("mic_gemm_bf16", int(a_mn), int(b_mn), _p(a), _ld(a), _p(b), _ld(b), M, N, K, _p(out), _ld(out),
+          int(d_f32), int(accumulate), _p(bias), ACT[act], _p(pre_act_out), _p(residual),
+          _ld(residual) if residual is not None else 0, block_n, group_m)
+    return out
+
+
+def lm_head_num_partials(V):
+    return lib().mic_lm_head_num_partials(V)
+
+
+def lm_head_ce_stats(h, emb, bias, labels, ws):
+    M, K = h.shape
+    V = emb.shape[0]
+    _call("mic_lm_head_ce_stats", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), _p(labels), M, V, K, _p(ws["pmax"]),
+          _p(ws["psum"]), _p(ws["psumz"]), _p(ws["zlabel"]))
+
+
+def ce_finalize(ws, mask, M, V, label_smoothing, with_loss=True):
+    _call("mic_ce_finalize", _p(ws["pmax"]), _p(ws["psum"]), _p(ws.get("psumz")), _p(ws.get("zlabel")), _p(mask),
+          ws["nparts"], M, V, float(label_smoothing), _p(ws["lse"]), _p(ws["row_loss"]) if with_loss else None,
+          _p(ws["row_w"]) if with_loss else None, _p(ws["out"]) if with_loss else None)
+
+
+def lm_head_ce_grad(h, emb, bias, labels, ws, conf, low, dlogits):
+    M, K = h.shape
+    V = emb.shape[0]
+    _call("mic_lm_head_ce_grad", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), _p(labels), _p(ws["lse"]),
+          _p(ws["row_w"]), float(conf), float(low), M, V, K, _p(dlogits), _ld(dlogits))
+
+
+def lm_head_search(h, emb, bias, mask_token, ws):
+    M, K = h.shape
+    V = emb.shape[0]
+    _call("mic_lm_head_search", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), int(mask_token), M, V, K,
+          _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]))
+
+
+def search_merge(ws, R):
+    _call("mic_search_merge", _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]), ws["nparts"],
+          R, _p(ws["row_lp"]), _p(ws["row_tok"]), _p(ws["row_ml"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / embedding / elementwise
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, out=None, mean=None, rstd=None):
+    M, d = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _call("mic_layernorm_fwd", _p(x), _p(gamma), _p(beta), float(eps), _p(out), _p(mean), _p(rstd), M, d)
+    return out
+
+
+def ln_bwd_workspace_floats(d):
+    return 2 * lib().mic_layernorm_bwd_num_partials() * d
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, workspace):
+    M, d = x.shape
+    _call("mic_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dgamma),
+          _p(dbeta), _p(workspace), M, d)
+    return dx
+
+
+def colsum_workspace_floats(M, N):
+    return lib().mic_colsum_num_chunks(M) * N
+
+
+def act_bwd_colsum(dy, u, act, du, dbias, workspace, accumulate=False):
+    M, N = dy.shape
+    _call("mic_act_bwd_colsum", _p(dy), _ld(dy), _p(u), _ld(u) if u is not None else 0, ACT[act], _p(du),
+          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), M, N)
+
+
+def embed_ln_fwd(ids, pos_ids, pos_mod, pos_offset, table, pos_table, scale, gamma, beta, eps, emb, out,
+                 mean=None, rstd=None):
+    M = ids.numel()
+    d = table.shape[1]
+    _call("mic_embed_ln_fwd", _p(ids), _p(pos_ids), int(pos_mod), int(pos_offset), _p(table), _p(pos_table),
+          float(scale), _p(gamma), _p(beta), float(eps), _p(emb), _p(out), _p(mean), _p(rstd), M, d)
+    return out
+
+
+def embed_bwd(ids, d_emb, scale, d_table, d_pos_rows, B, T):
+    d = d_emb.shape[-1]
+    _call("mic_embed_bwd", _p(ids), _p(d_emb), float(scale), _p(d_table), _p(d_pos_rows), B, T, d)
+
+
+def batch_sum(x, B, T, d, out, out_ld):
+    _call("mic_batch_sum", _p(x), B, T, d, _p(out), out_ld)
+
+
+def patchify(pixels, out, B, image_size, patch, channel_first=False, trunc_int=False):
+    assert pixels.dtype == F32 and pixels.is_contiguous()
+    _call("mic_patchify", _p(pixels), _p(out), B, image_size, patch, int(channel_first), int(trunc_int))
+    return out
+
+
+def vit_embed_ln_fwd(patch_out, patch_bias, cls, pos, gamma, beta, eps, use_ln, emb, out, mean, rstd, B, S):
+    d = patch_out.shape[1]
+    _call("mic_vit_embed_ln_fwd", _p(patch_out), _p(patch_bias), _p(cls), _p(pos), _p(gamma), _p(beta), float(eps),
+          int(use_ln), _p(emb), _p(out), _p(mean), _p(rstd), B, S, d)
+    return out
+
+
+def drop_cls_rows(d_emb, out, B, S):
+    d = d_emb.shape[-1]
+    _call("mic_drop_cls_rows", _p(d_emb), _p(out), B, S, d)
+    return out
+
+
+def adamw(p, m, v, g, shadow, hyper_dev):
+    _call("mic_adamw", _p(p), _p(m), _p(v), _p(g), _p(shadow), _p(hyper_dev), p.numel())
+
+
+def cast_f32_to_bf16(src, dst):
+    _call("mic_cast_f32_to_bf16", _p(src), _p(dst), src.numel())
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attention_fwd(q, k, v, out, lse, key_mask, causal, B, H, Tq, Tk, scale):
+    _call("mic_attention_fwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(out), _ld(out), _p(lse),
+          _p(key_mask), int(causal), B, H, Tq, Tk, 64, float(scale))
+    return out
+
+
+def attention_bwd(q, k, v, o, do, lse, key_mask, causal, dq, dk, dv, B, H, Tq, Tk, scale):
+    _call("mic_attention_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(do), _ld(do), _p(lse),
+          _p(key_mask), int(causal), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv), B, H, Tq, Tk, 64,
+          float(scale))
+
+
+def decode_attention(q, k_cache, v_cache, ldkv, ancestors, cache_len, n_keys, rows_per_kv, out, R, H, scale):
+    _call("mic_decode_attention", _p(q), _ld(q), _p(k_cache), _p(v_cache), int(ldkv), _p(ancestors), cache_len,
+          n_keys, rows_per_kv, _p(out), _ld(out), R, H, 64, float(scale))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# search steps
+# ------------------------------------------------------------------------------------------------
+def beam_step(ws, st, forced_token, B, K, L, V, cur_len, eos, early_stopping, length_penalty):
+    _call("mic_beam_step", _p(ws["row_lp"]), _p(ws["row_tok"]), int(forced_token), B, K, L, V, cur_len, eos,
+          int(early_stopping), float(length_penalty), _p(st["running_seq"]), _p(st["running_scores"]),
+          _p(st["sequences"]), _p(st["scores"]), _p(st["finished"]), _p(st["ancestors"]), _p(st["next_token"]),
+          _p(st["active"]))
+
+
+def beam_cond(st, B, K, cur_len, max_length, length_penalty, early_stopping):
+    _call("mic_beam_cond", _p(st["running_scores"]), _p(st["scores"]), _p(st["finished"]), B, K, cur_len, max_length,
+          float(length_penalty), int(early_stopping), _p(st["active"]))
+
+
+def beam_finalize(st, B, K, L, out_seq, out_scores):
+    _call("mic_beam_finalize", _p(st["sequences"]), _p(st["scores"]), _p(st["finished"]), _p(st["running_seq"]),
+          _p(st["running_scores"]), B, K, L, _p(out_seq), _p(out_scores))
+
+
+def greedy_step(ws, st, forced_token, R, L, cur_len, eos, pad):
+    _call("mic_greedy_step", _p(ws["row_tok"]), int(forced_token), R, L, cur_len, eos, pad, _p(st["sequences"]),
+          _p(st["finished"]), _p(st["next_token"]), _p(st["active"]))
+
+
+def greedy_cond(st, R, cur_len, max_length):
+    _call("mic_greedy_cond", _p(st["finished"]), R, cur_len, max_length, _p(st["active"]))
