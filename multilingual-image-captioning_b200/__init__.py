@@ -1,8 +1,31 @@
 """B200-native captioning hot path (CLIP-ViT -> mBART-50), drop-in for the reference's
-`FlaxCLIPVisionMBartForConditionalGeneration` API.  Import as `import mic_b200`."""
+`FlaxCLIPVisionMBartForConditionalGeneration` API.  Import as `import mic_b200`.
+
+Only configuration / synthetic data import eagerly (usable on a CPU-only box); the model, engine and
+training modules need CUDA + libmic_b200.so and are imported on first attribute access.
+"""
+import importlib
+
 from .configuration import (CLIPVisionConfig, MBartConfig, CLIPVisionMBartConfig, clip_mbart_config,
                             vit_bart_config, tiny_config)
 from . import synthetic
 
-__all__ = ["CLIPVisionConfig", "MBartConfig", "CLIPVisionMBartConfig", "clip_mbart_config",
-           "vit_bart_config", "tiny_config", "synthetic"]
+_LAZY = {
+    "FlaxCLIPVisionMBartForConditionalGeneration": ".modeling_clip_vision_mbart",
+    "Seq2SeqLMOutput": ".modeling_clip_vision_mbart",
+    "TrainState": ".training", "train_step": ".training", "eval_step": ".training",
+    "create_learning_rate_fn": ".training",
+}
+_LAZY_MODULES = ("ops", "engine", "generation", "training", "params", "modeling_clip_vision_mbart", "_lib")
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        return getattr(importlib.import_module(_LAZY[name], __name__), name)
+    if name in _LAZY_MODULES:
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError(name)
+
+
+__all__ = ["CLIPVisionConfig", "MBartConfig", "CLIPVisionMBartConfig", "clip_mbart_config", "vit_bart_config",
+           "tiny_config", "synthetic"] + list(_LAZY)

@@ -1,0 +1,348 @@
+"""Execution engine: sequences the sm_100a kernels (ops.py -> libmic_b200.so) for the training
+forward/backward of the captioning model and for the cached decode step.
+
+Reference call stack replaced: `train_step` main.py:684-707 -> `__call__`
+modeling_clip_vision_mbart.py:447-510 -> FlaxCLIPVisionModule / visual_projection / FlaxMBartDecoder /
+tied lm_head (:79-102,170-178) -> `loss_fn` main.py:658-680 -> `jax.value_and_grad` main.py:696.
+Backward is a hand-scheduled tape (no autograd): each Dense = dgrad GEMM + wgrad GEMM + bias column-sum.
+
+All activations are bf16 [tokens, features]; statistics and gradients of parameters are fp32.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from .params import ParamStore
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+class _Bufs:
+    """Lazily allocated, shape-keyed device buffers (allocated once per plan, reused every step)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t = {}
+
+    def get(self, name, shape, dtype=BF16):
+        key = name
+        t = self.t.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self.t[key] = t
+        return t
+
+    def nbytes(self):
+        return sum(x.numel() * x.element_size() for x in self.t.values())
+
+
+class CaptionEngine:
+    def __init__(self, config, store: ParamStore):
+        self.cfg = config
+        self.c = config.clip_vision_config
+        self.t = config.mbart_config
+        self.ps = store
+        self.dev = store.device
+        assert self.c.head_dim == 64 and self.t.head_dim == 64, "attention kernels are specialised for head_dim 64"
+        self.bufs = _Bufs(self.dev)
+        self.Vp = (self.t.vocab_size + 255) // 256 * 256
+        self.emb_scale = math.sqrt(self.t.d_model) if self.t.scale_embedding else 1.0
+        self._ws = None
+
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, floats):
+        if self._ws is None or self._ws.numel() < floats:
+            self._ws = torch.empty(int(floats), dtype=F32, device=self.dev)
+        return self._ws
+
+    def _ln_fwd(self, x, name, eps, out, stats=None):
+        ps = self.ps
+        mean, rstd = (stats if stats is not None else (None, None))
+        return ops.layernorm_fwd(x, ps.f(name + ".scale"), ps.f(name + ".bias"), eps, out=out, mean=mean, rstd=rstd)
+
+    def _ln_bwd(self, dy, x, name, stats, dres, dx):
+        ps = self.ps
+        d = x.shape[1]
+        ws = self._workspace(max(ops.ln_bwd_workspace_floats(d), 1))
+        ops.layernorm_bwd(dy, x, ps.f(name + ".scale"), stats[0], stats[1], dres, dx, ps.g(name + ".scale"),
+                          ps.g(name + ".bias"), ws)
+        return dx
+
+    def _dense_bwd(self, x, dy, wname, dx_out, bias=True, w_view=None, gw_view=None, gb_view=None, act=None, u=None,
+                   du=None):
+        """Backward of y = act(x @ W + b).  x: [M,K] input, dy: [M,N] grad of the output (post-act).
+        Returns dx (written into dx_out) — or None if dx_out is None."""
+        ps = self.ps
+        M, N = dy.shape
+        w = w_view if w_view is not None else ps.w(wname + ".w")
+        gw = gw_view if gw_view is not None else ps.g(wname + ".w")
+        gb = gb_view if gb_view is not None else (ps.g(wname + ".b") if bias else None)
+        ws = self._workspace(ops.colsum_workspace_floats(M, N))
+        if act is not None and act != "none":
+            ops.act_bwd_colsum(dy, u, act, du, gb, ws)
+            dy = du
+        elif gb is not None:
+            ops.act_bwd_colsum(dy, None, "none", None, gb, ws)
+        ops.gemm(x, dy, a_mn=True, b_mn=True, out=gw)                       # dW[K,N] = x^T dy
+        if dx_out is not None:
+            ops.gemm(dy, w, a_mn=False, b_mn=False, out=dx_out)               # dx[M,K] = dy W^T
+        return dx_out
+
+    # ------------------------------------------------------------------------------------------
+    # vision encoder + projection (forward).  save=True keeps what backward needs.
+    # ------------------------------------------------------------------------------------------
+    def encode(self, pixel_values, trunc_int=False, save=False, tag="enc"):
+        c, ps, b = self.c, self.ps, self.bufs
+        B = pixel_values.shape[0]
+        S, npatch, dv = c.num_tokens, c.num_patches, c.hidden_size
+        Mv = B * S
+        px = pixel_values.to(self.dev, F32).contiguous()
+        patches = ops.patchify(px, b.get(tag + ".patches", (B * npatch, c.patch_size ** 2 * 3)), B, c.image_size,
+                               c.patch_size, channel_first=c.channel_first_input, trunc_int=trunc_int)
+        patch_out = ops.gemm(patches, ps.w("v.patch.w"), b_mn=True, out=b.get(tag + ".patch_out", (B * npatch, dv)))
+        emb = b.get(tag + ".emb", (Mv, dv))
+        st_pre = (b.get(tag + ".pre.mean", (Mv,), F32), b.get(tag + ".pre.rstd", (Mv,), F32))
+        x = b.get(tag + ".x0", (Mv, dv))
+        ops.vit_embed_ln_fwd(patch_out, ps.f("v.patch.b") if c.patch_bias else None, ps.w("v.cls"), ps.w("v.pos"),
+                             ps.f("v.pre_ln.scale"), ps.f("v.pre_ln.bias"), c.layer_norm_eps, c.pre_layernorm, emb, x,
+                             st_pre[0], st_pre[1], B, S)
+        H = c.num_attention_heads
+        scale = 1.0 / math.sqrt(c.head_dim)
+        for l in range(c.num_hidden_layers):
+            n = f"v.{l}"
+            sfx = f".{l}" if save else ""
+            st1 = (b.get(tag + ".ln1.mean" + sfx, (Mv,), F32), b.get(tag + ".ln1.rstd" + sfx, (Mv,), F32))
+            a = self._ln_fwd(x, n + ".ln1", c.layer_norm_eps, b.get(tag + ".ln1" + sfx, (Mv, dv)), st1)
+            qkv = ops.gemm(a, ps.w(n + ".qkv.w"), b_mn=True, bias=ps.f(n + ".qkv.b"), out=b.get(tag + ".qkv" + sfx, (Mv, 3 * dv)))
+            att = b.get(tag + ".att" + sfx, (Mv, dv))
+            lse = b.get(tag + ".lse" + sfx, (B, H, S), F32)
+            ops.attention_fwd(qkv[:, :dv], qkv[:, dv:2 * dv], qkv[:, 2 * dv:], att, lse, None, False, B, H, S, S, scale)
+            xm = ops.gemm(att, ps.w(n + ".o.w"), b_mn=True, bias=ps.f(n + ".o.b"), residual=x,
+                          out=b.get(tag + ".xm" + sfx, (Mv, dv)))
+            st2 = (b.get(tag + ".ln2.mean" + sfx, (Mv,), F32), b.get(tag + ".ln2.rstd" + sfx, (Mv,), F32))
+            m = self._ln_fwd(xm, n + ".ln2", c.layer_norm_eps, b.get(tag + ".ln2" + sfx, (Mv, dv)), st2)
+            u = b.get(tag + ".u" + sfx, (Mv, c.intermediate_size)) if save else None
+            g = ops.gemm(m, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=c.hidden_act, pre_act_out=u,
+                         out=b.get(tag + ".g" + sfx, (Mv, c.intermediate_size)))
+            x = ops.gemm(g, ps.w(n + ".fc2.w"), b_mn=True, bias=ps.f(n + ".fc2.b"), residual=xm,
+                         out=b.get(tag + f".x{l + 1}" if save else tag + f".xping{l & 1}", (Mv, dv)))
+        if c.final_layernorm:
+            stf = (b.get(tag + ".post.mean", (Mv,), F32), b.get(tag + ".post.rstd", (Mv,), F32))
+            x = self._ln_fwd(x, "v.post_ln", c.layer_norm_eps, b.get(tag + ".post", (Mv, dv)), stf)
+        enc = ops.gemm(x, ps.w("proj.w"), b_mn=True, bias=ps.f("proj.b"), out=b.get(tag + ".out", (Mv, self.t.d_model)))
+        return enc
+
+    def cross_kv(self, enc, tag="enc"):
+        """All layers' cross-attention K/V projections of the visual tokens in one GEMM: [Mv, L*2d]."""
+        ps, t = self.ps, self.t
+        return ops.gemm(enc, ps.w("d.ca_kv.w"), b_mn=True, bias=ps.f("d.ca_kv.b"),
+                        out=self.bufs.get(tag + ".kv", (enc.shape[0], t.decoder_layers * 2 * t.d_model)))
+
+    # ------------------------------------------------------------------------------------------
+    # full-sequence decoder forward (training / eval), returns final hidden states [B*T, d]
+    # ------------------------------------------------------------------------------------------
+    def decoder_forward(self, ids, key_mask, pos_ids, enc_kv, B, T, S, save=False, tag="dec"):
+        t, ps, b = self.t, self.ps, self.bufs
+        d, M, H = t.d_model, B * T, t.decoder_attention_heads
+        assert t.pre_layernorm, "post-LN (BART) decoder: see engine_postln (config 5)"
+        eps = t.layer_norm_eps
+        scale = 1.0 / math.sqrt(t.head_dim)
+        emb = b.get(tag + ".emb", (M, d))
+        st = (b.get(tag + ".emb.mean", (M,), F32), b.get(tag + ".emb.rstd", (M,), F32))
+        x = b.get(tag + ".x0", (M, d))
+        ops.embed_ln_fwd(ids, pos_ids, T, t.position_offset, ps.w("shared"), ps.w("d.pos"), self.emb_scale,
+                         ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), eps, emb, x, st[0], st[1])
+        for l in range(t.decoder_layers):
+            n = f"d.{l}"
+            sfx = f".{l}" if save else ""
+            stA = (b.get(tag + ".lnA.mean" + sfx, (M,), F32), b.get(tag + ".lnA.rstd" + sfx, (M,), F32))
+            a = self._ln_fwd(x, n + ".ln_sa", eps, b.get(tag + ".lnA" + sfx, (M, d)), stA)
+            qkv = ops.gemm(a, ps.w(n + ".sa_qkv.w"), b_mn=True, bias=ps.f(n + ".sa_qkv.b"),
+                           out=b.get(tag + ".qkv" + sfx, (M, 3 * d)))
+            sa = b.get(tag + ".sa" + sfx, (M, d))
+            lse1 = b.get(tag + ".lse1" + sfx, (B, H, T), F32)
+            ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, lse1, key_mask, True, B, H, T, T, scale)
+            x1 = ops.gemm(sa, ps.w(n + ".sa_o.w"), b_mn=True, bias=ps.f(n + ".sa_o.b"), residual=x,
+                          out=b.get(tag + ".x1" + sfx, (M, d)))
+            stC = (b.get(tag + ".lnC.mean" + sfx, (M,), F32), b.get(tag + ".lnC.rstd" + sfx, (M,), F32))
+            cc = self._ln_fwd(x1, n + ".ln_ca", eps, b.get(tag + ".lnC" + sfx, (M, d)), stC)
+            qc = ops.gemm(cc, ps.w(n + ".ca_q.w"), b_mn=True, bias=ps.f(n + ".ca_q.b"), out=b.get(tag + ".qc" + sfx, (M, d)))
+            ca = b.get(tag + ".ca" + sfx, (M, d))
+            lse2 = b.get(tag + ".lse2" + sfx, (B, H, T), F32)
+            kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
+            vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+            ops.attention_fwd(qc, kl, vl, ca, lse2, None, False, B, H, T, S, scale)
+            x2 = ops.gemm(ca, ps.w(n + ".ca_o.w"), b_mn=True, bias=ps.f(n + ".ca_o.b"), residual=x1,
+                          out=b.get(tag + ".x2" + sfx, (M, d)))
+            stF = (b.get(tag + ".lnF.mean" + sfx, (M,), F32), b.get(tag + ".lnF.rstd" + sfx, (M,), F32))
+            f = self._ln_fwd(x2, n + ".ln_f", eps, b.get(tag + ".lnF" + sfx, (M, d)), stF)
+            u = b.get(tag + ".u" + sfx, (M, t.decoder_ffn_dim)) if save else None
+            g = ops.gemm(f, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=t.activation_function,
+                         pre_act_out=u, out=b.get(tag + ".g" + sfx, (M, t.decoder_ffn_dim)))
+            x = ops.gemm(g, ps.w(n + ".fc2.w"), b_mn=True, bias=ps.f(n + ".fc2.b"), residual=x2,
+                         out=b.get(tag + f".x{l + 1}" if save else tag + f".xping{l & 1}", (M, d)))
+        if t.final_layer_norm:
+            stL = (b.get(tag + ".lnL.mean", (M,), F32), b.get(tag + ".lnL.rstd", (M,), F32))
+            x = self._ln_fwd(x, "d.ln_final", eps, b.get(tag + ".hf", (M, d)), stL)
+        return x
+
+    # ------------------------------------------------------------------------------------------
+    # loss (fused lm_head + CE) and logits
+    # ------------------------------------------------------------------------------------------
+    def _ce_ws(self, M):
+        b, V = self.bufs, self.t.vocab_size
+        n = ops.lm_head_num_partials(V)
+        f = lambda nm, *s: b.get("ce." + nm, s, F32)
+        return {"nparts": n, "pmax": f("pmax", n, M), "psum": f("psum", n, M), "psumz": f("psumz", n, M),
+                "zlabel": f("zlabel", M), "lse": f("lse", M), "row_loss": f("row_loss", M), "row_w": f("row_w", M),
+                "out": f("out", 2)}
+
+    def loss_forward(self, hf, labels, mask, label_smoothing):
+        ps, V = self.ps, self.t.vocab_size
+        M = hf.shape[0]
+        ws = self._ce_ws(M)
+        ops.lm_head_ce_stats(hf, ps.w("shared"), ps.f("flb"), labels, ws)
+        ops.ce_finalize(ws, mask, M, V, label_smoothing)
+        return ws
+
+    def logits(self, hf):
+        """Materialised fp32 logits (B*T, V) for API parity with `__call__(...).logits`."""
+        ps, V = self.ps, self.t.vocab_size
+        out = torch.empty((hf.shape[0], V), dtype=F32, device=self.dev)
+        return ops.gemm(hf, ps.w("shared"), b_mn=False, bias=ps.f("flb"), out=out)
+
+    # ------------------------------------------------------------------------------------------
+    # training forward + backward: fills ps.grad, returns the CE workspace (ws["out"][0] = loss)
+    # ------------------------------------------------------------------------------------------
+    def forward_backward(self, pixel_values, decoder_input_ids, attention_mask, labels, label_smoothing=0.0,
+                         position_ids=None):
+        c, t, ps, b = self.c, self.t, self.ps, self.bufs
+        ps.ensure_grad()
+        B, T = decoder_input_ids.shape
+        S, dv, d = c.num_tokens, c.hidden_size, t.d_model
+        M, Mv = B * T, B * S
+        ids = decoder_input_ids.to(self.dev, I32).contiguous().view(-1)
+        km = attention_mask.to(self.dev, I32).contiguous()
+        lab = labels.to(self.dev, I32).contiguous().view(-1)
+        pos = None if position_ids is None else position_ids.to(self.dev, I32).contiguous().view(-1)
+        # ---------------- forward ----------------
+        enc = self.encode(pixel_values, trunc_int=False, save=True, tag="tr.enc")
+        enc_kv = self.cross_kv(enc, tag="tr.enc")
+        hf = self.decoder_forward(ids, km, pos, enc_kv, B, T, S, save=True, tag="tr.dec")
+        ws = self.loss_forward(hf, lab, km.view(-1), label_smoothing)
+        # ---------------- backward: lm_head + CE ----------------
+        V = t.vocab_size
+        conf, low = 1.0 - label_smoothing, label_smoothing / (V - 1)
+        dlog = b.get("tr.dlogits", (M, self.Vp))
+        ops.lm_head_ce_grad(hf, ps.w("shared"), ps.f("flb"), lab, ws, conf, low, dlog)
+        cws = self._workspace(ops.colsum_workspace_floats(M, self.Vp))
+        flb_pad = b.get("tr.dflb", (self.Vp,), F32)
+        ops.act_bwd_colsum(dlog, None, "none", None, flb_pad, cws)
+        ps.g("flb").copy_(flb_pad[:V])
+        ops.gemm(dlog[:, :V], hf, a_mn=True, b_mn=True, out=ps.g("shared"))          # dE = dlogits^T h
+        dx = b.get("tr.dx", (M, d))
+        dhf = ops.gemm(dlog[:, :V], ps.w("shared"), a_mn=False, b_mn=True, out=b.get("tr.dhf", (M, d)))
+        tg = "tr.dec"
+        if t.final_layer_norm:
+            self._ln_bwd(dhf, b.t[tg + f".x{t.decoder_layers}"], "d.ln_final",
+                         (b.t[tg + ".lnL.mean"], b.t[tg + ".lnL.rstd"]), None, dx)
+        else:
+            dx.copy_(dhf)
+        # ---------------- backward: decoder layers ----------------
+        H = t.decoder_attention_heads
+        scale = 1.0 / math.sqrt(t.head_dim)
+        dg = b.get("tr.dg", (M, t.decoder_ffn_dim))
+        du = b.get("tr.du", (M, t.decoder_ffn_dim))
+        dtmp = b.get("tr.dtmp", (M, d))
+        dqkv = b.get("tr.dqkv", (M, 3 * d))
+        dqc = b.get("tr.dqc", (M, d))
+        d_enc_kv = b.get("tr.d_enc_kv", (Mv, t.decoder_layers * 2 * d))
+        for l in reversed(range(t.decoder_layers)):
+            n = f"d.{l}"
+            sfx = f".{l}"
+            g_, u_, lnF = b.t[tg + ".g" + sfx], b.t[tg + ".u" + sfx], b.t[tg + ".lnF" + sfx]
+            x2, x1, x0 = b.t[tg + ".x2" + sfx], b.t[tg + ".x1" + sfx], b.t[tg + f".x{l}"]
+            # FFN
+            self._dense_bwd(g_, dx, n + ".fc2", dg)
+            self._dense_bwd(lnF, dg, n + ".fc1", dtmp, act=t.activation_function, u=u_, du=du)
+            self._ln_bwd(dtmp, x2, n + ".ln_f", (b.t[tg + ".lnF.mean" + sfx], b.t[tg + ".lnF.rstd" + sfx]), dx, dx)
+            # cross attention
+            ca, qc, lnC = b.t[tg + ".ca" + sfx], b.t[tg + ".qc" + sfx], b.t[tg + ".lnC" + sfx]
+            self._dense_bwd(ca, dx, n + ".ca_o", dtmp)
+            kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
+            vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+            ops.attention_bwd(qc, kl, vl, ca, dtmp, b.t[tg + ".lse2" + sfx], None, False, dqc,
+                              d_enc_kv[:, l * 2 * d: l * 2 * d + d], d_enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d],
+                              B, H, T, S, scale)
+            self._dense_bwd(lnC, dqc, n + ".ca_q", dtmp)
+            self._ln_bwd(dtmp, x1, n + ".ln_ca", (b.t[tg + ".lnC.mean" + sfx], b.t[tg + ".lnC.rstd" + sfx]), dx, dx)
+            # self attention
+            sa, qkv, lnA = b.t[tg + ".sa" + sfx], b.t[tg + ".qkv" + sfx], b.t[tg + ".lnA" + sfx]
+            self._dense_bwd(sa, dx, n + ".sa_o", dtmp)
+            ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, dtmp, b.t[tg + ".lse1" + sfx], km, True,
+                              dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, T, T, scale)
+            self._dense_bwd(lnA, dqkv, n + ".sa_qkv", dtmp)
+            self._ln_bwd(dtmp, x0, n + ".ln_sa", (b.t[tg + ".lnA.mean" + sfx], b.t[tg + ".lnA.rstd" + sfx]), dx, dx)
+        # embedding
+        demb = self._ln_bwd(dx, b.t[tg + ".emb"], "d.ln_emb", (b.t[tg + ".emb.mean"], b.t[tg + ".emb.rstd"]), None, dtmp)
+        gpos = ps.g("d.pos")
+        gpos.zero_()
+        if pos is None:
+            ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), gpos[t.position_offset:], B, T)
+        else:
+            ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), None, B, T)
+            gpos.index_add_(0, (pos + t.position_offset).long(), demb.float())   # rare path (explicit position ids)
+        # ---------------- backward: cross K/V projection, visual projection ----------------
+        d_enc = b.get("tr.d_enc", (Mv, d))
+        self._dense_bwd(enc, d_enc_kv, "d.ca_kv", d_enc)
+        te = "tr.enc"
+        L = c.num_hidden_layers
+        x_last = b.t[te + ".post"] if c.final_layernorm else b.t[te + f".x{L}"]
+        dxv = b.get("tr.dxv", (Mv, dv))
+        self._dense_bwd(x_last, d_enc, "proj", dxv)
+        dvt = b.get("tr.dvt", (Mv, dv))
+        if c.final_layernorm:
+            self._ln_bwd(dxv, b.t[te + f".x{L}"], "v.post_ln", (b.t[te + ".post.mean"], b.t[te + ".post.rstd"]), None, dvt)
+            dxv, dvt = dvt, dxv
+        else:
+            ps.g("v.post_ln.scale").zero_()      # dead parameters (pooled output unused): zero gradient
+            ps.g("v.post_ln.bias").zero_()
+        # ---------------- backward: vision layers ----------------
+        Hv = c.num_attention_heads
+        vscale = 1.0 / math.sqrt(c.head_dim)
+        dgv = b.get("tr.dgv", (Mv, c.intermediate_size))
+        duv = b.get("tr.duv", (Mv, c.intermediate_size))
+        dqkvv = b.get("tr.dqkvv", (Mv, 3 * dv))
+        for l in reversed(range(L)):
+            n = f"v.{l}"
+            sfx = f".{l}"
+            g_, u_, ln2 = b.t[te + ".g" + sfx], b.t[te + ".u" + sfx], b.t[te + ".ln2" + sfx]
+            xm, x0 = b.t[te + ".xm" + sfx], b.t[te + f".x{l}"]
+            self._dense_bwd(g_, dxv, n + ".fc2", dgv)
+            self._dense_bwd(ln2, dgv, n + ".fc1", dvt, act=c.hidden_act, u=u_, du=duv)
+            self._ln_bwd(dvt, xm, n + ".ln2", (b.t[te + ".ln2.mean" + sfx], b.t[te + ".ln2.rstd" + sfx]), dxv, dxv)
+            att, qkv, ln1 = b.t[te + ".att" + sfx], b.t[te + ".qkv" + sfx], b.t[te + ".ln1" + sfx]
+            self._dense_bwd(att, dxv, n + ".o", dvt)
+            ops.attention_bwd(qkv[:, :dv], qkv[:, dv:2 * dv], qkv[:, 2 * dv:], att, dvt, b.t[te + ".lse" + sfx], None,
+                              False, dqkvv[:, :dv], dqkvv[:, dv:2 * dv], dqkvv[:, 2 * dv:], B, Hv, S, S, vscale)
+            self._dense_bwd(ln1, dqkvv, n + ".qkv", dvt)
+            self._ln_bwd(dvt, x0, n + ".ln1", (b.t[te + ".ln1.mean" + sfx], b.t[te + ".ln1.rstd" + sfx]), dxv, dxv)
+        # embeddings: pre-LN, class / position / patch kernel
+        if c.pre_layernorm:
+            demb_v = self._ln_bwd(dxv, b.t[te + ".emb"], "v.pre_ln", (b.t[te + ".pre.mean"], b.t[te + ".pre.rstd"]),
+                                  None, dvt)
+        else:
+            demb_v = dxv
+            ps.g("v.pre_ln.scale").zero_()
+            ps.g("v.pre_ln.bias").zero_()
+        ops.batch_sum(demb_v, B, S, dv, ps.g("v.pos"), dv)
+        ps.g("v.cls").copy_(ps.g("v.pos")[0])
+        dpo = ops.drop_cls_rows(demb_v, b.get("tr.dpo", (B * (S - 1), dv)), B, S)
+        if c.patch_bias:
+            ops.act_bwd_colsum(dpo, None, "none", None, ps.g("v.patch.b"), self._workspace(
+                ops.colsum_workspace_floats(dpo.shape[0], dv)))
+        ops.gemm(b.t[te + ".patches"], dpo, a_mn=True, b_mn=True, out=ps.g("v.patch.w"))
+        return ws

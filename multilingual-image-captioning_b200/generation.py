@@ -1,0 +1,155 @@
+"""KV-cached decode step and the greedy / beam-search drivers.
+
+Replaces `generation_clip_vision_utils.py` (`generate` :128-336, `_greedy_search` :422-535,
+`_beam_search` :665-990) and the cached `decode` path (`modeling_clip_vision_mbart.py:249-282,519-693`).
+Differences in mechanism, not in results:
+  * cross-attention K/V of the visual tokens are projected once per image (the reference re-projects
+    them every step) and shared by the beams of an image;
+  * the self-attention cache is never gathered on beam reorder (:945-953): beams carry an ancestor table;
+  * the loop runs a fixed trip count with a device-side `active` flag mirroring the while_loop
+    condition, so the host never synchronises inside the loop (CUDA-graph capturable).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+class DecodeCache:
+    """Device state of the cached decoder: self-attention K|V per layer, cross K|V, ancestor table."""
+
+    def __init__(self, engine, rows, max_length, enc_kv, rows_per_image, use_ancestors):
+        t = engine.t
+        dev = engine.dev
+        self.rows, self.T, self.rows_per_image = rows, max_length, rows_per_image
+        self.self_kv = engine.bufs.get("gen.self_kv", (t.decoder_layers, rows, max_length, 2 * t.d_model))
+        self.enc_kv = enc_kv
+        self.ancestors = None
+        if use_ancestors:
+            self.ancestors = torch.arange(rows, dtype=I32, device=dev)[:, None].expand(rows, max_length).contiguous()
+        self.index = 0
+
+
+def decode_step(engine, cache: DecodeCache, tokens, pos: int):
+    """One token per row through the decoder; returns final hidden states [R, d]."""
+    t, ps, b = engine.t, engine.ps, engine.bufs
+    assert t.pre_layernorm, "cached decode is implemented for the pre-LN (mBART) decoder"
+    R, d, H, T = cache.rows, t.d_model, t.decoder_attention_heads, cache.T
+    S = engine.c.num_tokens
+    eps = t.layer_norm_eps
+    scale = 1.0 / math.sqrt(t.head_dim)
+    x = b.get("gen.x", (R, d))
+    # every row sits at the same position: pos_mod=1 -> position = 0 + (pos + offset)
+    ops.embed_ln_fwd(tokens, None, 1, pos + t.position_offset, ps.w("shared"), ps.w("d.pos"), engine.emb_scale,
+                     ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), eps, None, x)
+    a = b.get("gen.a", (R, d))
+    q = b.get("gen.q", (R, d))
+    o = b.get("gen.o", (R, d))
+    g = b.get("gen.g", (R, t.decoder_ffn_dim))
+    L2 = t.decoder_layers * 2 * d
+    for l in range(t.decoder_layers):
+        n = f"d.{l}"
+        wqkv, bqkv = ps.w(n + ".sa_qkv.w"), ps.f(n + ".sa_qkv.b")
+        engine._ln_fwd(x, n + ".ln_sa", eps, a)
+        ops.gemm(a, wqkv[:, :d], b_mn=True, bias=bqkv[:d], out=q)
+        kv_slot = cache.self_kv[l, :, pos, :]                      # [R, 2d] view, row pitch T*2d: written in place
+        ops.gemm(a, wqkv[:, d:], b_mn=True, bias=bqkv[d:], out=kv_slot)
+        kc = cache.self_kv[l].view(R * T, 2 * d)
+        ops.decode_attention(q, kc[:, :d], kc[:, d:], 2 * d, cache.ancestors, T, pos + 1, 1, o, R, H, scale)
+        ops.gemm(o, ps.w(n + ".sa_o.w"), b_mn=True, bias=ps.f(n + ".sa_o.b"), residual=x, out=x)
+        engine._ln_fwd(x, n + ".ln_ca", eps, a)
+        ops.gemm(a, ps.w(n + ".ca_q.w"), b_mn=True, bias=ps.f(n + ".ca_q.b"), out=q)
+        ek = cache.enc_kv[:, l * 2 * d: l * 2 * d + d]
+        ev = cache.enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+        ops.decode_attention(q, ek, ev, L2, None, S, S, cache.rows_per_image, o, R, H, scale)
+        ops.gemm(o, ps.w(n + ".ca_o.w"), b_mn=True, bias=ps.f(n + ".ca_o.b"), residual=x, out=x)
+        engine._ln_fwd(x, n + ".ln_f", eps, a)
+        ops.gemm(a, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=t.activation_function, out=g)
+        ops.gemm(g, ps.w(n + ".fc2.w"), b_mn=True, bias=ps.f(n + ".fc2.b"), residual=x, out=x)
+    if t.final_layer_norm:
+        return engine._ln_fwd(x, "d.ln_final", eps, b.get("gen.hf", (R, d)))
+    return x
+
+
+def _search_ws(engine, R):
+    b, V = engine.bufs, engine.t.vocab_size
+    n = ops.lm_head_num_partials(V)
+    return {"nparts": n, "pmax": b.get("gen.pmax", (n, R), F32), "psum": b.get("gen.psum", (n, R), F32),
+            "cand_val": b.get("gen.cand_val", (n, R, 8), F32), "cand_idx": b.get("gen.cand_idx", (n, R, 8), I32),
+            "row_lp": b.get("gen.row_lp", (R, 8), F32), "row_tok": b.get("gen.row_tok", (R, 8), I32),
+            "row_ml": b.get("gen.row_ml", (R, 2), F32)}
+
+
+def _forced_token(cur_len, max_length, forced_bos, forced_eos):
+    """FlaxForcedBOS (cur_len == 1) then FlaxForcedEOS (cur_len == max_length-1): the later processor wins."""
+    f = -1
+    if forced_bos is not None and cur_len == 1:
+        f = forced_bos
+    if forced_eos is not None and cur_len == max_length - 1:
+        f = forced_eos
+    return f
+
+
+@torch.no_grad()
+def generate(engine, pixel_values, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams,
+             min_length, forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping):
+    """`generate` :128-336.  encode() truncates pixels to int32 first (modeling_clip_vision_mbart.py:330)."""
+    t, ps = engine.t, engine.ps
+    dev = engine.dev
+    B = pixel_values.shape[0]
+    K, Lmax, V = num_beams, max_length, t.vocab_size
+    if K > 4:
+        raise NotImplementedError("beam-step kernel keeps 2*num_beams <= 8 candidates (num_beams <= 4)")
+    R = B * K
+    enc = engine.encode(pixel_values, trunc_int=True, save=False, tag="gen.enc")
+    enc_kv = engine.cross_kv(enc, tag="gen.enc")
+    cache = DecodeCache(engine, R, Lmax, enc_kv, K, use_ancestors=K > 1)
+    ws = _search_ws(engine, R)
+    active = torch.ones(1, dtype=I32, device=dev)
+    next_token = torch.full((R,), decoder_start_token_id, dtype=I32, device=dev)
+    mask_eos = min_length is not None and eos_token_id is not None and min_length > -1
+
+    if K == 1:
+        st = {"sequences": torch.full((R, Lmax), pad_token_id, dtype=I32, device=dev),
+              "finished": torch.zeros(R, dtype=I32, device=dev), "next_token": next_token, "active": active}
+        st["sequences"][:, 0] = decoder_start_token_id
+        for cur_len in range(1, Lmax):
+            forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
+            last = cur_len == Lmax - 1
+            if not (last and forced >= 0):
+                hf = decode_step(engine, cache, st["next_token"], cur_len - 1)
+            if forced < 0:
+                mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
+                ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mt, ws)
+                ops.search_merge(ws, R)
+            ops.greedy_step(ws, st, forced, R, Lmax, cur_len, eos_token_id, pad_token_id)
+            ops.greedy_cond(st, R, cur_len + 1, Lmax)
+        return {"sequences": st["sequences"]}
+
+    st = {"running_seq": torch.full((B, K, Lmax), pad_token_id, dtype=I32, device=dev),
+          "sequences": torch.full((B, K, Lmax), pad_token_id, dtype=I32, device=dev),
+          "running_scores": torch.tensor([0.0] + [-1.0e7] * (K - 1), dtype=F32, device=dev).repeat(B, 1).contiguous(),
+          "scores": torch.full((B, K), -1.0e7, dtype=F32, device=dev),
+          "finished": torch.zeros((B, K), dtype=I32, device=dev),
+          "ancestors": cache.ancestors, "next_token": next_token, "active": active}
+    st["running_seq"][:, :, 0] = decoder_start_token_id
+    for cur_len in range(1, Lmax):
+        forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
+        last = cur_len == Lmax - 1
+        if not (last and forced >= 0):
+            hf = decode_step(engine, cache, st["next_token"], cur_len - 1)
+        if forced < 0:
+            mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
+            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mt, ws)
+            ops.search_merge(ws, R)
+        ops.beam_step(ws, st, forced, B, K, Lmax, V, cur_len, eos_token_id, early_stopping, length_penalty)
+        ops.beam_cond(st, B, K, cur_len + 1, Lmax, length_penalty, early_stopping)
+    out_seq = torch.empty((B, Lmax), dtype=I32, device=dev)
+    out_scores = torch.empty((B,), dtype=F32, device=dev)
+    ops.beam_finalize(st, B, K, Lmax, out_seq, out_scores)
+    return {"sequences": out_seq, "scores": out_scores}

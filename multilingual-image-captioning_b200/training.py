@@ -1,0 +1,128 @@
+"""Training step of the reference (`main.py:684-707`) on the B200 engine.
+
+  train_step:  loss, grad = value_and_grad(compute_loss)(params)      main.py:688-697
+               grad = lax.pmean(grad, "batch")                          main.py:698   -> NCCL all-reduce / N
+               state.apply_gradients(grads=grad)  (optax.adamw)         main.py:701,629-635
+               metrics = pmean({"loss", "learning_rate"})               main.py:703-704
+
+Data parallelism = one process per GPU (torch.distributed, NCCL over NVLink); every rank holds a full
+replica; the gradient all-reduce is an UNWEIGHTED mean of the per-rank token-normalised gradients, as
+`pmean` does (main.py:679,698).  The all-reduce runs bucket by bucket over the flat gradient buffer.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+F32 = torch.float32
+
+
+def create_learning_rate_fn(train_ds_size, train_batch_size, num_train_epochs, num_warmup_steps, learning_rate):
+    """main.py:281-292: linear warm-up 0 -> lr over `num_warmup_steps`, then linear decay to 0."""
+    steps_per_epoch = train_ds_size // train_batch_size
+    num_train_steps = steps_per_epoch * num_train_epochs
+
+    def schedule(step):
+        if step < num_warmup_steps:
+            return learning_rate * step / max(num_warmup_steps, 1)
+        frac = (step - num_warmup_steps) / max(num_train_steps - num_warmup_steps, 1)
+        return learning_rate * (1.0 - min(max(frac, 0.0), 1.0))
+    return schedule
+
+
+def bucketed_allreduce_sum(flat: torch.Tensor, bucket_elems: int):
+    """In-place SUM all-reduce of a flat buffer in fixed-size buckets (launch-latency sized, not link sized:
+    NVSwitch gives every peer full bandwidth).  Works for any backend (NCCL on GPU, gloo in the CPU tests)."""
+    n = flat.numel()
+    handles = []
+    for lo in range(0, n, bucket_elems):
+        handles.append(dist.all_reduce(flat[lo:min(n, lo + bucket_elems)], op=dist.ReduceOp.SUM, async_op=True))
+    for h in handles:
+        h.wait()
+
+
+class TrainState:
+    """flax TrainState analogue (main.py:247-251,638): params + AdamW state + step, living on the GPU."""
+
+    def __init__(self, model, learning_rate_fn, b1=0.9, b2=0.999, eps=1e-8, weight_decay=0.0,
+                 bucket_bytes=256 << 20):
+        self.model = model
+        self.store = model.store
+        self.store.ensure_optimizer()
+        self.learning_rate_fn = learning_rate_fn
+        self.b1, self.b2, self.eps, self.weight_decay = b1, b2, eps, weight_decay
+        self.step = 0
+        self.hp_host = torch.zeros(8, dtype=F32).pin_memory()
+        self.hp_dev = torch.zeros(8, dtype=F32, device=self.store.device)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.bucket_elems = max(int(bucket_bytes) // 4, 1)
+        self.metrics_buf = torch.zeros(2, dtype=F32, device=self.store.device)
+
+    @classmethod
+    def create(cls, apply_fn=None, params=None, tx=None, model=None, **kw):
+        return cls(model, **kw)
+
+    @property
+    def params(self):
+        return self.store.tree()
+
+    @property
+    def opt_state(self):
+        return {"count": self.step, "mu": self.store.tree(self.store.adam_m), "nu": self.store.tree(self.store.adam_v)}
+
+    def allreduce_grads(self):
+        """lax.pmean(grad, 'batch'): SUM over ranks here, the 1/N is folded into the AdamW kernel."""
+        if self.world == 1:
+            return
+        bucketed_allreduce_sum(self.store.grad, self.bucket_elems)
+
+    def apply_gradients(self):
+        """optax.adamw with the schedule evaluated at the pre-increment count."""
+        count = self.step
+        t = count + 1
+        lr = float(self.learning_rate_fn(count))
+        self.hp_host[0] = lr
+        self.hp_host[1] = self.b1
+        self.hp_host[2] = self.b2
+        self.hp_host[3] = self.eps
+        self.hp_host[4] = self.weight_decay
+        self.hp_host[5] = 1.0 / (1.0 - self.b1 ** t)
+        self.hp_host[6] = 1.0 / (1.0 - self.b2 ** t)
+        self.hp_host[7] = 1.0 / self.world
+        self.hp_dev.copy_(self.hp_host, non_blocking=True)
+        s = self.store
+        ops.adamw(s.master, s.adam_m, s.adam_v, s.grad, s.shadow, self.hp_dev)
+        self.step = t
+        return lr
+
+
+@torch.no_grad()
+def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0):
+    """One optimisation step.  batch keys as the reference's collate output (main.py:493-523):
+    pixel_values (B,H,W,3) f32, input_ids = labels (B,T), attention_mask (B,T), decoder_input_ids (B,T).
+    Returns (state, metrics) with metrics = {"loss": 0-d tensor, "learning_rate": float}."""
+    eng = state.model.engine
+    dev = state.store.device
+    ws = eng.forward_backward(torch.as_tensor(batch["pixel_values"]).to(dev), torch.as_tensor(batch["decoder_input_ids"]),
+                              torch.as_tensor(batch["attention_mask"]), torch.as_tensor(batch["input_ids"]),
+                              label_smoothing=label_smoothing_factor)
+    state.allreduce_grads()
+    lr = state.apply_gradients()
+    loss = ws["out"][0:1].clone()
+    if state.world > 1:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+        loss /= state.world
+    return state, {"loss": loss[0], "learning_rate": lr}
+
+
+@torch.no_grad()
+def eval_step(model, batch, label_smoothing_factor: float = 0.0):
+    """main.py:710-721."""
+    loss = model.loss(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"], batch["input_ids"],
+                      label_smoothing_factor)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+        loss = loss / dist.get_world_size()
+    return {"loss": loss}
