@@ -26,8 +26,19 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+TIMED = {}          # C-ABI name -> list of (start, end) CUDA events recorded around each call (bench.py)
+
+
 def _call(name, *args):
     LAUNCHES[0] += 1
+    ev = TIMED.get(name)
+    if ev is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(getattr(lib(), name)(_s(), *args), name)
+        e.record()
+        ev.append((s, e))
+        return
     check(getattr(lib(), name)(_s(), *args), name)
 
 
