@@ -1,0 +1,106 @@
+"""Golden-vector tests.  CPU: the oracle reproduces the committed fixtures (regression pin).  GPU: the
+CUDA path reproduces the same fixtures — including BASELINE configs[0] at FULL size (B=8, V=250,054) —
+without running the oracle on the GPU box.  Fixtures come from tests/golden/gen_golden.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mic_b200
+from mic_b200 import synthetic
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _tiny_setup():
+    cfg = mic_b200.tiny_config(vocab_size=1003, layers=2)
+    params = synthetic.make_params(cfg, seed=1, perturbed=True, std=0.05)
+    batch = synthetic.make_batch(cfg, 4, seq_len=16, seed=0, min_len=4)
+    return cfg, params, batch
+
+
+def test_oracle_reproduces_tiny_golden():
+    from oracle import reference_model as rm
+    from oracle import reference_generate as rg
+    gold = np.load(os.path.join(G, "tiny_golden.npz"))
+    cfg, params, batch = _tiny_setup()
+    p = rm.to_torch_tree(params)
+    with torch.no_grad():
+        logits = rm.forward_logits(p, batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"], None, cfg)
+    np.testing.assert_allclose(logits.numpy(), gold["logits"], atol=2e-5, rtol=1e-5)
+    loss, grads, _ = rm.loss_and_grads(params, batch, cfg, 0.1)
+    assert abs(loss - float(gold["loss_eps0.1"])) < 1e-5
+    np.testing.assert_allclose(grads["model"]["visual_projection"]["kernel"], gold["grad_proj_kernel"], atol=1e-6, rtol=1e-4)
+    gp = synthetic.make_params(cfg, seed=5, perturbed=True, std=0.3)
+    gb = synthetic.make_batch(cfg, 3, seq_len=16, seed=0, min_len=4)
+    for beams in (1, 4):
+        r = rg.generate(gp, gb["pixel_values"], cfg, num_beams=beams, max_length=12, forced_bos_token_id=1001)
+        np.testing.assert_array_equal(r["sequences"], gold[f"seq_beams{beams}"])
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_tiny_golden():
+    gold = np.load(os.path.join(G, "tiny_golden.npz"))
+    cfg, params, batch = _tiny_setup()
+    model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg)
+    model.params = params
+    logits = model(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"]).logits.float().cpu().numpy()
+    assert np.abs(logits - gold["logits"]).max() / np.abs(gold["logits"]).max() < 3e-2
+    for eps in (0.0, 0.1):
+        loss = float(model.loss(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"],
+                                batch["input_ids"], eps))
+        assert abs(loss - float(gold[f"loss_eps{eps}"])) < 2e-2
+    model.store.ensure_grad()
+    model.engine.forward_backward(torch.from_numpy(batch["pixel_values"]), torch.from_numpy(batch["decoder_input_ids"]),
+                                  torch.from_numpy(batch["attention_mask"]), torch.from_numpy(batch["input_ids"]), 0.1)
+    grads = model.store.to_numpy_tree(model.store.grad)
+    flat = dict(("/".join(k), v) for k, v in synthetic.tree_flatten(grads))
+    norms = np.array([np.linalg.norm(flat[k]) for k in gold["grad_names"]])
+    np.testing.assert_allclose(norms, gold["gradnorms_eps0.1"], rtol=0.05, atol=1e-5)
+    g = flat["model/visual_projection/kernel"]
+    assert np.linalg.norm(g - gold["grad_proj_kernel"]) / np.linalg.norm(gold["grad_proj_kernel"]) < 0.05
+    gp = synthetic.make_params(cfg, seed=5, perturbed=True, std=0.3)
+    gb = synthetic.make_batch(cfg, 3, seq_len=16, seed=0, min_len=4)
+    model.params = gp
+    seq1 = model.generate(gb["pixel_values"], num_beams=1, max_length=12, forced_bos_token_id=1001).sequences.cpu().numpy()
+    margins = gold["margins_beams1"]
+    for b in range(3):
+        for pos in range(1, 12):
+            if 2 <= pos < 11 and margins[b, pos - 1] < 0.05:
+                break
+            assert seq1[b, pos] == gold["seq_beams1"][b, pos]
+    seq4 = model.generate(gb["pixel_values"], num_beams=4, max_length=12, forced_bos_token_id=1001).sequences.cpu().numpy()
+    for b in range(3):
+        if gold["clear_beams4"][b]:
+            np.testing.assert_array_equal(seq4[b], gold["seq_beams4"][b])
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_full_size_config1_golden():
+    """BASELINE configs[0]: full CLIP-ViT-B/32 + mBART-50, batch 8, 64 tokens, random init (seeded)."""
+    gold = np.load(os.path.join(G, "config1_full_golden.npz"))
+    cfg = mic_b200.clip_mbart_config()
+    params = synthetic.make_params(cfg, seed=1, perturbed=False)
+    batch = synthetic.make_batch(cfg, 8, 64, seed=0)
+    model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, _do_init=False)
+    model.params = params
+    del params
+    out = model(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"])
+    logits = out.logits
+    assert tuple(logits.shape) == tuple(gold["shape"]) == (8, 64, 250054)          # inference.py:30
+    cols = torch.from_numpy(gold["cols"]).to(logits.device)
+    sl = logits[:, :, cols].float().cpu().numpy()
+    rel = np.abs(sl - gold["logits_slice"]).max() / float(gold["logits_absmax"])
+    assert rel < 3e-2, rel                                                          # bf16 mode
+    lse = torch.logsumexp(logits.float(), -1).cpu().numpy()
+    np.testing.assert_allclose(lse, gold["lse"], atol=2e-2)
+    # greedy-style decisions: argmax must agree wherever the oracle's top-2 gap exceeds the bf16 tolerance
+    am = logits.argmax(-1).cpu().numpy()
+    clear = gold["top2_gap"] > 0.1
+    assert clear.mean() > 0.3
+    assert (am[clear] == gold["argmax"][clear]).all()
+    for eps in (0.0, 0.1):
+        loss = float(model.loss(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"],
+                                batch["input_ids"], eps))
+        assert abs(loss - float(gold[f"loss_eps{eps}"])) < 2e-2, (eps, loss, float(gold[f"loss_eps{eps}"]))
