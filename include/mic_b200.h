@@ -35,11 +35,12 @@ int mic_abi_version(void);
  * visual_projection modeling_clip_vision_mbart.py:53-59,90 [E6], FlaxMBartAttention / FFN [D2-D4],
  * patch conv as GEMM [E1], and all their dgrad / wgrad contractions under jax.value_and_grad
  * main.py:696 [L2].  D is bf16 (d_is_f32=0) or fp32; accumulate=1 adds into an fp32 D.
- * D2 (optional, bf16, ld = ldd) receives the pre-activation.  block_n/group_m = 0 -> auto. */
+ * D2 (optional, bf16, ld = ldd) receives the pre-activation.  block_n/group_m/split_k = 0 -> auto
+ * (split_k > 1 cuts K into slices combined by TMA reduce-add; fp32 outputs only). */
 int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
                   long long ldb, int M, int N, int K, void* D, long long ldd, int d_is_f32, int accumulate,
                   const float* bias, int act, void* D2, const void* residual, long long ldr, int block_n,
-                  int group_m);
+                  int group_m, int split_k);
 
 /* ---- tied lm_head fused with log-softmax / label-smoothed CE ------------------------------------
  * modeling_clip_vision_mbart.py:170-178 [H1] + loss_fn main.py:658-680 [L1]; fp32 logits never reach HBM.

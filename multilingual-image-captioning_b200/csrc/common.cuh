@@ -80,14 +80,26 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 #define MIC_ACT_NONE 0
 #define MIC_ACT_GELU 1
 #define MIC_ACT_QUICK_GELU 2
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): 2 MUFU + ~10 FMA
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-ax * ax * 1.4426950408889634f);
+  return copysignf(fmaf(-p, e, 1.0f), x);
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == MIC_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  if (act == MIC_ACT_GELU) return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
   if (act == MIC_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
   return x;
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {  // d act / dx
   if (act == MIC_ACT_GELU) {
-    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
     float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
   }
@@ -146,6 +158,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// TMA bulk tensor STORE (smem -> global), bulk-group completion.  The smem source must be visible to the
+// async proxy (fence_proxy_async after the st.shared writes) before one thread issues the copy.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// fp32 reduce-add variant (D += tile)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed groups of this thread have finished READING their smem source (buffer reusable)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
@@ -222,6 +254,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
 // host: TMA descriptor encode (driver entry point fetched through the runtime; no -lcuda needed)
 // ------------------------------------------------------------------------------------------------
 // 2-D bf16 tensor, `inner` contiguous elements, row pitch `ld` elements, 128B swizzle.
-int mic_make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                          uint32_t box_inner, uint32_t box_outer);
+int mic_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer);
+inline int mic_make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                                 uint32_t box_inner, uint32_t box_outer) {
+  return mic_make_tmap_2d(out, ptr, 2, inner, outer, ld, box_inner, box_outer);
+}
 int mic_num_sms();

@@ -46,20 +46,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int mic_make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                          uint32_t box_inner, uint32_t box_outer) {
+int mic_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   MIC_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   MIC_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand pointer %p not 16-byte aligned", ptr);
-  MIC_CHECK_ARG(ld % 8 == 0, "TMA operand leading dimension %llu not a multiple of 8 elements",
-                (unsigned long long)ld);
+  MIC_CHECK_ARG((ld * elem_bytes) % 16 == 0, "TMA operand row pitch %llu elements x %d B not a multiple of 16 bytes",
+                (unsigned long long)ld, elem_bytes);
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MIC_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u",
                 (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner,
                 box_outer);
@@ -80,7 +80,10 @@ static int pick_block_n(int M, int N, int forced) {
     const int bn = cands[i];
     const long long tiles = (long long)mb * ((N + bn - 1) / bn);
     const long long waves = (tiles + sms - 1) / sms;
-    const double cost = (double)waves * bn * (1.0 + 6.0 / bn);   // mild preference for wide tiles
+    // 128-wide tiles re-read A from smem twice as often per FLOP (UMMA operand bandwidth bound):
+    // measured ~0.65x / 0.9x the 256-wide MMA rate on B200
+    const double eff = bn == 256 ? 1.0 : (bn == 192 ? 0.9 : 0.65);
+    const double cost = (double)waves * bn / eff;
     if (cost < best_cost) {
       best_cost = cost;
       best = bn;
@@ -90,7 +93,7 @@ static int pick_block_n(int M, int N, int forced) {
 }
 
 struct Operands {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, td, td2;
   Shape shape;
   int bn;
 };
@@ -98,6 +101,8 @@ struct Operands {
 static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb,
                           int M, int N, int K, int block_n, int group_m) {
   MIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
+  memset(&o->td, 0, sizeof(CUtensorMap));
+  memset(&o->td2, 0, sizeof(CUtensorMap));
   o->bn = pick_block_n(M, N, block_n);
   int rc;
   if (!a_mn)
@@ -119,6 +124,8 @@ static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long l
   if (group_m <= 0) group_m = ((long long)M * K * 2 <= (48ll << 20)) ? s.num_m_blocks : 16;
   s.group_m = group_m < s.num_m_blocks ? group_m : s.num_m_blocks;
   if (s.group_m < 1) s.group_m = 1;
+  s.split_k = 1;
+  s.kb_per_split = (K + BLOCK_K - 1) / BLOCK_K;
   return MIC_OK;
 }
 
@@ -130,9 +137,9 @@ static int launch_one(cudaStream_t stream, const Operands& o, const typename Epi
     MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks;
+  const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks * o.shape.split_k;
   const int grid = tiles < mic_num_sms() ? tiles : mic_num_sms();
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.shape, ep);
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.td, o.td2, o.shape, ep);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
@@ -149,7 +156,7 @@ static int launch_bn(cudaStream_t stream, const Operands& o, const typename Epi:
 extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, long long lda,
                              const void* B, long long ldb, int M, int N, int K, void* D, long long ldd, int d_is_f32,
                              int accumulate, const float* bias, int act, void* D2, const void* residual,
-                             long long ldr, int block_n, int group_m) {
+                             long long ldr, int block_n, int group_m, int split_k) {
   Operands o;
   int rc = setup_operands(&o, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, block_n, group_m);
   if (rc) return rc;
@@ -167,12 +174,48 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
   ep.ldr = ldr;
   ep.out_scale = 1.0f;
   const int esz = d_is_f32 ? 4 : 2;
-  bool vec = ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((ldd * esz) % 16 == 0);
-  if (bias) vec = vec && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-  if (D2) vec = vec && ((reinterpret_cast<uintptr_t>(D2) & 15) == 0) && (ldd % 8 == 0);
-  if (residual) vec = vec && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) && (ldr % 8 == 0);
-  ep.vec_ok = vec ? 1 : 0;
+  bool tma = ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((ldd * esz) % 16 == 0) && (N % 8 == 0);
+  if (bias) tma = tma && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  if (D2) tma = tma && ((reinterpret_cast<uintptr_t>(D2) & 15) == 0) && (ldd % 8 == 0);
+  if (residual) tma = tma && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) && (ldr % 8 == 0);
+  ep.tma_ok = tma ? 1 : 0;
+  if (tma) {
+    // output tiles leave through 32-row x 128-byte boxes (64 bf16 or 32 fp32 columns)
+    rc = mic_make_tmap_2d(&o.td, D, esz, N, M, ldd, d_is_f32 ? 32 : 64, 32);
+    if (rc) return rc;
+    if (D2) {
+      rc = mic_make_tmap_2d(&o.td2, D2, 2, N, M, ldd, 64, 32);
+      if (rc) return rc;
+    }
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // ---- split-K (fp32 outputs only): fills the machine when M*N yields less than a wave of tiles ----
+  const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
+  const bool can_split = d_is_f32 && tma && !bias && act == MIC_ACT_NONE && !D2 && !residual;
+  if (split_k == 0) {          // auto
+    split_k = 1;
+    if (can_split) {
+      const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks, sms = mic_num_sms();
+      double best = (double)((tiles + sms - 1) / sms);
+      for (int sk = 2; sk <= 16; ++sk) {
+        if (nkb / sk < 8) break;                     // keep >= 512 of K per slice
+        const double cost = (double)((tiles * sk + sms - 1) / sms) / sk + 0.02 * sk;
+        if (cost < best - 1e-9) {
+          best = cost;
+          split_k = sk;
+        }
+      }
+    }
+  }
+  if (split_k > 1) {
+    MIC_CHECK_ARG(can_split, "split_k needs a plain fp32 TMA-storable output (no bias/act/residual)");
+    o.shape.kb_per_split = (nkb + split_k - 1) / split_k;
+    o.shape.split_k = (nkb + o.shape.kb_per_split - 1) / o.shape.kb_per_split;
+    if (o.shape.split_k > 1) {
+      if (!accumulate) MIC_CHECK_CUDA(cudaMemset2DAsync(D, ldd * 4, 0, (size_t)N * 4, M, s));
+      ep.accumulate = 1;
+    }
+  }
   if (!a_mn_major && b_mn_major) return launch_bn<0, 1, EpiStore>(s, o, ep);
   if (!a_mn_major && !b_mn_major) return launch_bn<0, 0, EpiStore>(s, o, ep);
   if (a_mn_major && b_mn_major) return launch_bn<1, 1, EpiStore>(s, o, ep);
@@ -204,6 +247,8 @@ extern "C" int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, c
   if (rc) return rc;
   // cover the padded columns too so they are written as zeros
   o.shape.num_n_blocks = (int)(ldd / 256);
+  rc = mic_make_tmap_2d(&o.td, dlogits, 2, ldd, M, ldd, 64, 32);
+  if (rc) return rc;
   EpiCEGradParams ep = {bias, labels, lse, row_w, conf, low, reinterpret_cast<bf16*>(dlogits), ldd};
   return launch_one<0, 0, 256, EpiCEGrad>(reinterpret_cast<cudaStream_t>(stream), o, ep);
 }

@@ -10,7 +10,10 @@
 // the CE backward (dlogits) and the beam-search candidate selection.
 //
 // Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 spare,
-// w4..w11 epilogue (two warps per TMEM lane quarter, each takes half of the tile's columns).
+// w4..w11 epilogue.  An epilogue warp owns one TMEM lane quarter (32 rows) and a share of the tile's
+// 64-column groups.  Outputs leave through a warp-private 4 KB swizzled staging buffer and TMA bulk
+// stores (coalesced, asynchronous, tails clipped by the tensor map); residual tiles enter through the
+// same buffer with coalesced 16-byte loads.
 #pragma once
 
 #include "common.cuh"
@@ -23,6 +26,8 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
+constexpr int GROUP_COLS = 64;          // epilogue granularity: 64 accumulator columns
+constexpr int STG_BYTES = 4096;         // per-warp staging: 32 rows x 128 B
 
 template <int BN>
 struct Cfg {
@@ -30,14 +35,18 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int COLS_PER_WARP = BN / 2;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : 6);
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * STG_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int NUM_GROUPS = BN / GROUP_COLS;
+  static constexpr int GROUPS_HALF0 = (NUM_GROUPS + 1) / 2;
 };
 
 struct Shape {
   int M, N, K;
   int num_m_blocks, num_n_blocks, group_m;
+  int split_k;        // >1: K is cut into `split_k` slices, one work unit each, combined by TMA reduce-add
+  int kb_per_split;   // k-blocks per slice
 };
 
 struct TileCoord {
@@ -56,6 +65,37 @@ __device__ __forceinline__ TileCoord tile_coord(const Shape& s, int t) {
   return c;
 }
 
+// per-call context handed to the epilogue policies
+struct EpiCtx {
+  int row;       // global row owned by this thread
+  int row0;      // first global row of the warp's 32-row slab
+  int lane;
+  uint8_t* stg;  // warp-private staging buffer (1024-byte aligned)
+  const CUtensorMap* tmap_d;
+  const CUtensorMap* tmap_d2;
+};
+
+// swizzled (SWIZZLE_128B) address of 16-byte unit `u` of row `r` in a [32 x 128 B] staging tile
+__device__ __forceinline__ uint8_t* stg_addr(uint8_t* stg, int r, int u) { return stg + r * 128 + ((u ^ (r & 7)) << 4); }
+
+// make the staging buffer writable again: the issuing lane waits until earlier TMA stores have read it
+__device__ __forceinline__ void stg_acquire(int lane) {
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+}
+// publish the staging buffer (written with st.shared by all lanes) through a TMA store
+__device__ __forceinline__ void stg_store(const CUtensorMap* map, uint8_t* stg, int lane, int c0, int r0, bool reduce_add) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce_add)
+      tma_reduce_add_2d(map, stg, c0, r0);
+    else
+      tma_store_2d(map, stg, c0, r0);
+    tma_store_commit();
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // Epilogue policy 0: store with optional bias / activation / residual / accumulate
 // --------------------------------------------------------------------------------------------
@@ -64,13 +104,13 @@ struct EpiStoreParams {
   long long ldd;
   int d_f32;            // 1: fp32 output
   int accumulate;       // fp32 only: D += result
-  int vec_ok;           // pointers/strides allow 16-byte vector access
+  int tma_ok;           // outputs reachable by TMA (16-byte aligned pitch / base) and N % 8 == 0
   const float* bias;    // [N] fp32 or null
   int act;              // MIC_ACT_*
   bf16* D2;             // optional pre-activation copy (bf16, same ld as D) or null
   const bf16* residual; // optional bf16 [M, ldr] added after activation
   long long ldr;
-  float out_scale;      // applied to (acc + bias) before activation (1.0 normally)
+  float out_scale;      // applied to acc before the bias (1.0 normally)
 };
 
 struct EpiStore {
@@ -78,74 +118,117 @@ struct EpiStore {
   struct State {};
   __device__ static void tile_begin(const Params&, State&, const Shape&, int, int, int) {}
   __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
-  // v: 32 consecutive columns [col0, col0+32) of row `row`
-  __device__ static void chunk(const Params& p, State&, const Shape& s, int row, int col0, float* v) {
+
+  // scalar fallback (unaligned outputs / odd N): v = 32 consecutive columns [col0, col0+32) of row `row`
+  __device__ static void chunk_scalar(const Params& p, const Shape& s, int row, int col0, const float* v) {
     if (row >= s.M || col0 >= s.N) return;
-    const bool full = (col0 + 32 <= s.N) && p.vec_ok;
-    if (full) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = col0 + g * 8;
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] * p.out_scale;
-        if (p.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + c);
-          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
-          x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-          x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-        }
-        if (p.D2) {
-          uint4 u = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                               pack_bf16(x[6], x[7]));
-          *reinterpret_cast<uint4*>(p.D2 + (long long)row * p.ldd + c) = u;
-        }
-        if (p.act != MIC_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = act_fwd(x[j], p.act);
-        }
-        if (p.residual) {
-          const uint4 r = *reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + c);
-          float2 f;
-          f = unpack_bf16(r.x); x[0] += f.x; x[1] += f.y;
-          f = unpack_bf16(r.y); x[2] += f.x; x[3] += f.y;
-          f = unpack_bf16(r.z); x[4] += f.x; x[5] += f.y;
-          f = unpack_bf16(r.w); x[6] += f.x; x[7] += f.y;
-        }
-        if (p.d_f32) {
-          float* d = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + c;
-          float4 o0 = make_float4(x[0], x[1], x[2], x[3]);
-          float4 o1 = make_float4(x[4], x[5], x[6], x[7]);
-          if (p.accumulate) {
-            const float4 a0 = *reinterpret_cast<const float4*>(d);
-            const float4 a1 = *reinterpret_cast<const float4*>(d + 4);
-            o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
-            o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
-          }
-          *reinterpret_cast<float4*>(d) = o0;
-          *reinterpret_cast<float4*>(d + 4) = o1;
-        } else {
-          uint4 u = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                               pack_bf16(x[6], x[7]));
-          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + c) = u;
-        }
+    for (int j = 0; j < 32; ++j) {
+      const int c = col0 + j;
+      if (c >= s.N) continue;
+      float x = v[j] * p.out_scale;
+      if (p.bias) x += p.bias[c];
+      if (p.D2) p.D2[(long long)row * p.ldd + c] = __float2bfloat16_rn(x);
+      x = act_fwd(x, p.act);
+      if (p.residual) x += __bfloat162float(p.residual[(long long)row * p.ldr + c]);
+      if (p.d_f32) {
+        float* d = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + c;
+        *d = p.accumulate ? (*d + x) : x;
+      } else {
+        reinterpret_cast<bf16*>(p.D)[(long long)row * p.ldd + c] = __float2bfloat16_rn(x);
       }
-    } else {
+    }
+  }
+
+  // v: 64 consecutive columns [col0, col0+64) of row ctx.row (fp32 accumulators)
+  __device__ static void group(const Params& p, State&, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+    if (col0 >= s.N) return;                      // warp-uniform
+    if (!p.tma_ok) {
+      chunk_scalar(p, s, ctx.row, col0, v);
+      chunk_scalar(p, s, ctx.row, col0 + 32, v + 32);
+      return;
+    }
+    const int lane = ctx.lane;
+    uint8_t* stg = ctx.stg;
+    // ---- residual tile: coalesced 16-byte loads -> swizzled staging -> registers ----
+    uint4 res[8];
+    if (p.residual) {
+      stg_acquire(lane);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = col0 + j;
-        if (c >= s.N) continue;
-        float x = v[j] * p.out_scale;
-        if (p.bias) x += p.bias[c];
-        if (p.D2) p.D2[(long long)row * p.ldd + c] = __float2bfloat16_rn(x);
-        x = act_fwd(x, p.act);
-        if (p.residual) x += __bfloat162float(p.residual[(long long)row * p.ldr + c]);
-        if (p.d_f32) {
-          float* d = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + c;
-          *d = p.accumulate ? (*d + x) : x;
-        } else {
-          reinterpret_cast<bf16*>(p.D)[(long long)row * p.ldd + c] = __float2bfloat16_rn(x);
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3), u = lane & 7;
+        const int grow = ctx.row0 + r, c = col0 + u * 8;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (grow < s.M && c < s.N) val = *reinterpret_cast<const uint4*>(p.residual + (long long)grow * p.ldr + c);
+        *reinterpret_cast<uint4*>(stg_addr(stg, r, u)) = val;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) res[u] = *reinterpret_cast<const uint4*>(stg_addr(stg, lane, u));
+      __syncwarp();
+    }
+    // ---- bias (vector loads; N % 8 == 0 on this path so a unit is all-in or all-out) ----
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = col0 + u * 8;
+      float4 b0 = make_float4(0, 0, 0, 0), b1 = b0;
+      if (p.bias && c < s.N) {
+        b0 = *reinterpret_cast<const float4*>(p.bias + c);
+        b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+      }
+      float* x = v + u * 8;
+      x[0] = x[0] * p.out_scale + b0.x; x[1] = x[1] * p.out_scale + b0.y;
+      x[2] = x[2] * p.out_scale + b0.z; x[3] = x[3] * p.out_scale + b0.w;
+      x[4] = x[4] * p.out_scale + b1.x; x[5] = x[5] * p.out_scale + b1.y;
+      x[6] = x[6] * p.out_scale + b1.z; x[7] = x[7] * p.out_scale + b1.w;
+    }
+    // ---- optional pre-activation copy ----
+    if (p.D2) {
+      stg_acquire(lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* x = v + u * 8;
+        *reinterpret_cast<uint4*>(stg_addr(stg, lane, u)) =
+            make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      }
+      stg_store(ctx.tmap_d2, stg, lane, col0, ctx.row0, false);
+    }
+    if (p.act != MIC_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = act_fwd(v[j], p.act);
+    }
+    if (p.residual) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float* x = v + u * 8;
+        float2 f;
+        f = unpack_bf16(res[u].x); x[0] += f.x; x[1] += f.y;
+        f = unpack_bf16(res[u].y); x[2] += f.x; x[3] += f.y;
+        f = unpack_bf16(res[u].z); x[4] += f.x; x[5] += f.y;
+        f = unpack_bf16(res[u].w); x[6] += f.x; x[7] += f.y;
+      }
+    }
+    if (!p.d_f32) {
+      stg_acquire(lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* x = v + u * 8;
+        *reinterpret_cast<uint4*>(stg_addr(stg, lane, u)) =
+            make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      }
+      stg_store(ctx.tmap_d, stg, lane, col0, ctx.row0, false);
+    } else {
+      // fp32: two 32-column (128-byte) halves through the same buffer
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (col0 + hh * 32 >= s.N) break;        // warp-uniform
+        stg_acquire(lane);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float* x = v + hh * 32 + u * 4;
+          *reinterpret_cast<float4*>(stg_addr(stg, lane, u)) = make_float4(x[0], x[1], x[2], x[3]);
         }
+        stg_store(ctx.tmap_d, stg, lane, col0 + hh * 32, ctx.row0, p.accumulate != 0);
       }
     }
   }
@@ -164,6 +247,8 @@ struct EpiCEStatsParams {
   float* zlabel;         // [M]
 };
 
+#define MIC_LOG2E 1.4426950408889634f
+
 struct EpiCEStats {
   typedef EpiCEStatsParams Params;
   struct State {
@@ -176,28 +261,45 @@ struct EpiCEStats {
     st.sz = 0.f;
     st.label = (row < s.M) ? p.labels[row] : -1;
   }
-  __device__ static void chunk(const Params& p, State& st, const Shape& s, int row, int col0, float* v) {
-    if (row >= s.M || col0 >= s.N) return;
-    float cmax = -INFINITY;
+  __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+    if (col0 >= s.N) return;                      // warp-uniform
+    const bool full = col0 + 64 <= s.N;
+    const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    if (full && (bias_vec || !p.bias)) {
+      if (p.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = col0 + j;
-      float z = v[j];
-      if (c < s.N) {
-        if (p.bias) z += p.bias[c];
-        st.sz += z;
-        if (c == st.label) p.zlabel[row] = z;
-      } else {
-        z = -INFINITY;
+        for (int u = 0; u < 16; ++u) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + u * 4);
+          v[u * 4 + 0] += b.x; v[u * 4 + 1] += b.y; v[u * 4 + 2] += b.z; v[u * 4 + 3] += b.w;
+        }
       }
-      v[j] = z;
-      cmax = fmaxf(cmax, z);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int c = col0 + j;
+        v[j] = (c < s.N) ? (p.bias ? v[j] + p.bias[c] : v[j]) : -INFINITY;
+      }
     }
+    const unsigned rel = static_cast<unsigned>(st.label - col0);
+    if (rel < 64u && ctx.row < s.M) {              // the label's logit lives in this group (rare)
+      float zy = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) zy = (rel == static_cast<unsigned>(j)) ? v[j] : zy;
+      p.zlabel[ctx.row] = zy;
+    }
+    float cmax = v[0], csum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      cmax = fmaxf(cmax, v[j]);
+      csum += full ? v[j] : ((col0 + j < s.N) ? v[j] : 0.f);
+    }
+    st.sz += csum;
     const float nm = fmaxf(st.mx, cmax);
+    const float nm2 = nm * MIC_LOG2E;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc += __expf(v[j] - nm);
-    st.sm = st.sm * __expf(st.mx - nm) + acc;
+    for (int j = 0; j < 64; ++j) acc += exp2f(fmaf(v[j], MIC_LOG2E, -nm2));
+    st.sm = st.sm * exp2f((st.mx - nm) * MIC_LOG2E) + acc;
     st.mx = nm;
   }
   __device__ static void tile_end(const Params& p, State& st, const Shape& s, int row, int, int n_blk, int half) {
@@ -220,52 +322,69 @@ struct EpiCEGradParams {
   const float* row_w;    // [M]  mask / sum(mask) (0 for padded targets)
   float conf, low;       // soft-label values
   bf16* dlogits;         // [M, ldd]
-  long long ldd;         // multiple of 8; columns [N, ldd) are written as zero
+  long long ldd;         // multiple of 256; columns [N, ldd) are written as zero
 };
 
 struct EpiCEGrad {
   typedef EpiCEGradParams Params;
   struct State {
-    float lse, w;
+    float lse2, w;
     int label;
   };
   __device__ static void tile_begin(const Params& p, State& st, const Shape& s, int row, int, int) {
     const bool ok = row < s.M;
-    st.lse = ok ? p.lse[row] : 0.f;
+    st.lse2 = ok ? p.lse[row] * MIC_LOG2E : 0.f;
     st.w = ok ? p.row_w[row] : 0.f;
     st.label = ok ? p.labels[row] : -1;
   }
-  __device__ static void chunk(const Params& p, State& st, const Shape& s, int row, int col0, float* v) {
-    if (row >= s.M || col0 >= p.ldd) return;
-    bf16* out = p.dlogits + (long long)row * p.ldd + col0;
+  __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+    if (col0 >= p.ldd) return;                    // warp-uniform
+    const bool full = col0 + 64 <= s.N;
+    const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    if (full && (bias_vec || !p.bias)) {
+      if (p.bias) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = col0 + g * 8 + j;
-        float z = v[g * 8 + j];
-        float d = 0.f;
-        if (c < s.N) {
-          if (p.bias) z += p.bias[c];
-          const float pr = __expf(z - st.lse);
-          d = (pr - ((c == st.label) ? p.conf : p.low)) * st.w;
+        for (int u = 0; u < 16; ++u) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + u * 4);
+          v[u * 4 + 0] += b.x; v[u * 4 + 1] += b.y; v[u * 4 + 2] += b.z; v[u * 4 + 3] += b.w;
         }
-        x[j] = d;
       }
-      if (col0 + g * 8 + 8 <= p.ldd) {
-        *reinterpret_cast<uint4*>(out + g * 8) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
-                                                            pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int c = col0 + j;
+        v[j] = (c < s.N) ? (p.bias ? v[j] + p.bias[c] : v[j]) : -INFINITY;   // exp2(-inf) = 0
       }
     }
+    const float lw = p.low * st.w;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = fmaf(exp2f(fmaf(v[j], MIC_LOG2E, -st.lse2)), st.w, -lw);
+    if (!full) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = (col0 + j < s.N) ? v[j] : 0.f;     // padded vocab columns: exactly zero
+    }
+    const unsigned rel = static_cast<unsigned>(st.label - col0);
+    if (rel < 64u) {
+      const float fix = (p.low - p.conf) * st.w;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] += (rel == static_cast<unsigned>(j)) ? fix : 0.f;
+    }
+    stg_acquire(ctx.lane);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float* x = v + u * 8;
+      *reinterpret_cast<uint4*>(stg_addr(ctx.stg, ctx.lane, u)) =
+          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    }
+    stg_store(ctx.tmap_d, ctx.stg, ctx.lane, col0, ctx.row0, false);
   }
   __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
 };
 
 // --------------------------------------------------------------------------------------------
 // Epilogue policy 3: decode-time lm_head for search: per (row, column-half) partial log-softmax
-// statistics + the TOPK best (value, index) of the half tile.  Used by greedy (TOPK=1 semantics via
-// k=2*beams>=2) and beam search; a follow-up kernel merges the partial lists (beam.cu).
+// statistics + the TOPK best (value, index) of the half tile; a follow-up kernel merges the partial
+// lists (beam.cu).
 // --------------------------------------------------------------------------------------------
 constexpr int SEARCH_TOPK = 8;
 struct EpiSearchParams {
@@ -293,11 +412,11 @@ struct EpiSearch {
       st.ti[i] = 0x7fffffff;
     }
   }
-  __device__ static void chunk(const Params& p, State& st, const Shape& s, int row, int col0, float* v) {
-    if (row >= s.M || col0 >= s.N) return;
+  __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+    if (col0 >= s.N) return;
     float cmax = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 64; ++j) {
       const int c = col0 + j;
       float z = v[j];
       if (c < s.N && c != p.mask_token) {
@@ -325,9 +444,10 @@ struct EpiSearch {
       }
     }
     const float nm = fmaxf(st.mx, cmax);
+    if (nm == -INFINITY) return;                   // every column masked so far
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc += __expf(v[j] - nm);
+    for (int j = 0; j < 64; ++j) acc += __expf(v[j] - nm);
     st.sm = st.sm * __expf(st.mx - nm) + acc;
     st.mx = nm;
   }
@@ -350,6 +470,7 @@ struct EpiSearch {
 template <int A_MN, int B_MN, int BN, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d2,
             const Shape shape, const typename Epi::Params ep) {
   typedef Cfg<BN> C;
   extern __shared__ uint8_t smem_raw[];
@@ -357,7 +478,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // 1024B alignment for SWIZZLE_128B
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
@@ -367,6 +489,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = shape.num_m_blocks * shape.num_n_blocks;
+  const int num_units = num_tiles * shape.split_k;
   const int num_k_blocks = (shape.K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -395,10 +518,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(shape, t);
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const TileCoord tc = tile_coord(shape, u % num_tiles);
         const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int kb0 = (u / num_tiles) * shape.kb_per_split;
+        const int kb1 = min(kb0 + shape.kb_per_split, num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
@@ -438,12 +563,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int kb0 = (u / num_tiles) * shape.kb_per_split;
+        const int kb1 = min(kb0 + shape.kb_per_split, num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
@@ -452,10 +579,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = umma_smem_desc(a_addr + k * a_kstep, a_lbo, a_sbo);
             const uint64_t db = umma_smem_desc(b_addr + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0) || (k > 0));
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -467,29 +594,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - 4;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;           // which half of the tile's columns
+    const int half = ew >> 2;           // which share of the tile's 64-column groups
+    const int g_begin = half == 0 ? 0 : C::GROUPS_HALF0;
+    const int g_end = half == 0 ? C::GROUPS_HALF0 : C::NUM_GROUPS;
+    EpiCtx ctx;
+    ctx.lane = lane;
+    ctx.stg = smem_epi + ew * STG_BYTES;
+    ctx.tmap_d = &tmap_d;
+    ctx.tmap_d2 = &tmap_d2;
     uint32_t it = 0;
     typename Epi::State st;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const TileCoord tc = tile_coord(shape, t);
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+      const TileCoord tc = tile_coord(shape, u % num_tiles);
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int row = tc.m_blk * BLOCK_M + quarter * 32 + lane;
-      Epi::tile_begin(ep, st, shape, row, tc.m_blk, tc.n_blk);
+      ctx.row0 = tc.m_blk * BLOCK_M + quarter * 32;
+      ctx.row = ctx.row0 + lane;
+      Epi::tile_begin(ep, st, shape, ctx.row, tc.m_blk, tc.n_blk);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * C::COLS_PER_WARP;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < C::COLS_PER_WARP / 32; ++c) {
-        float v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
+      for (int g = g_begin; g < g_end; ++g) {
+        float v[GROUP_COLS];
+        tmem_ld_32x32(taddr + g * GROUP_COLS, v);
+        tmem_ld_32x32(taddr + g * GROUP_COLS + 32, v + 32);
         tmem_ld_wait();
-        Epi::chunk(ep, st, shape, row, tc.n_blk * BN + half * C::COLS_PER_WARP + c * 32, v);
+        if (g == g_end - 1) {                      // accumulator drained: hand the TMEM buffer back early
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        Epi::group(ep, st, shape, ctx, tc.n_blk * BN + g * GROUP_COLS, v);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      Epi::tile_end(ep, st, shape, row, tc.m_blk, tc.n_blk, half);
+      Epi::tile_end(ep, st, shape, ctx.row, tc.m_blk, tc.n_blk, half);
     }
+    if (lane == 0) tma_store_wait_all();            // staged tiles fully written before the CTA retires
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -51,7 +51,7 @@ def _ld(t):
 # GEMM family
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, act="none", pre_act_out=None,
-         residual=None, accumulate=False, block_n=0, group_m=0):
+         residual=None, accumulate=False, block_n=0, group_m=0, split_k=0):
     """D[M,N] = act(A[M,K] B[N,K]^T + bias) + residual.
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True, Flax kernel)."""
     assert a.dtype == BF16 and b.dtype == BF16
@@ -74,7 +74,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, a
         assert bias.dtype == F32 and bias.numel() == N
     _call("mic_gemm_bf16", int(a_mn), int(b_mn), _p(a), _ld(a), _p(b), _ld(b), M, N, K, _p(out), _ld(out),
           int(d_f32), int(accumulate), _p(bias), ACT[act], _p(pre_act_out), _p(residual),
-          _ld(residual) if residual is not None else 0, block_n, group_m)
+          _ld(residual) if residual is not None else 0, block_n, group_m, split_k)
     return out
 
 

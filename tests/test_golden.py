@@ -57,7 +57,8 @@ def test_cuda_path_reproduces_tiny_golden():
     grads = model.store.to_numpy_tree(model.store.grad)
     flat = dict(("/".join(k), v) for k, v in synthetic.tree_flatten(grads))
     norms = np.array([np.linalg.norm(flat[k]) for k in gold["grad_names"]])
-    np.testing.assert_allclose(norms, gold["gradnorms_eps0.1"], rtol=0.05, atol=1e-5)
+    gn = gold["gradnorms_eps0.1"]
+    np.testing.assert_allclose(norms, gn, rtol=0.05, atol=2e-3 * float(gn.max()))   # k_proj bias grads are ~0 analytically
     g = flat["model/visual_projection/kernel"]
     assert np.linalg.norm(g - gold["grad_proj_kernel"]) / np.linalg.norm(gold["grad_proj_kernel"]) < 0.05
     gp = synthetic.make_params(cfg, seed=5, perturbed=True, std=0.3)

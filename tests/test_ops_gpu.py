@@ -357,3 +357,18 @@ def test_lm_head_search_and_merge():
     assert (got_tok[clear] == idx[clear]).all()
     assert clear.mean() > 0.9
     np.testing.assert_allclose(got_lp[clear], val[clear], atol=2e-4)
+
+
+@pytest.mark.parametrize("split_k", [0, 3, 8])
+def test_gemm_split_k_reduce_add(split_k):
+    """wgrad-shaped GEMM (few output tiles, long K) with K slices combined by TMA reduce-add."""
+    tokens, din, dout = 4096, 256, 384
+    x, dy = rnd(tokens, din, seed=90), rnd(tokens, dout, seed=91)
+    out = torch.full((din, dout), 3.0, dtype=torch.float32, device=DEV)      # must be overwritten, not added to
+    ops.gemm(x, dy, a_mn=True, b_mn=True, out=out, split_k=split_k)
+    torch.cuda.synchronize()
+    want = x.float().t() @ dy.float()
+    close(out, want, 0.5, 1e-2, f"split_k={split_k}")
+    ops.gemm(x, dy, a_mn=True, b_mn=True, out=out, split_k=split_k, accumulate=True)
+    torch.cuda.synchronize()
+    close(out, 2 * want, 1.0, 1e-2, f"split_k={split_k} accumulate")
