@@ -158,21 +158,28 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    # ---- timed region 1: inputs resident in HBM ----
+    # ---- timed region 1: inputs resident in HBM (forward+backward replayed as one CUDA graph) ----
     ops.LAUNCHES[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # live timing of the dominant kernel (fused lm_head + CE statistics GEMM) on the launching stream
-    ops.TIMED["mic_lm_head_ce_stats"] = []
     e0.record()
-    loss = None
     for i in range(args.steps):
         _, metrics = mic_b200.train_step(state, devb)
-        loss = metrics["loss"]
     e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    # ---- instrumented eager pass over the same steps: live CUDA-event timing of the dominant kernel
+    # (fused lm_head + CE statistics GEMM) on the launching stream, and the launch count of one step ----
+    ops.TIMED["mic_lm_head_ce_stats"] = []
+    ops.LAUNCHES[0] = 0
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for i in range(args.steps):
+        mic_b200.train_step(state, devb, use_cuda_graph=False)
+    e5.record()
     barrier()
     k_ev = ops.TIMED.pop("mic_lm_head_ce_stats")
     launches = ops.LAUNCHES[0]
-    ms = e0.elapsed_time(e1) / args.steps
+    ms_eager = e4.elapsed_time(e5) / args.steps
     k_ms = sum(s.elapsed_time(e) for s, e in k_ev) / len(k_ev)
     # ---- timed region 2: end to end through the public API with host buffers ----
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -210,7 +217,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "CLIP-ViT-B/32 + mBART-50 training step (fwd+bwd+AdamW), 224x224 images, "
                                "64-token captions", "per_gpu_batch": B, "global_batch": B * world, "seq_len": T,
-                   "parallelism": f"dp{world}", "dropout": 0.0, "l2": "working set (>20 GB/step) exceeds the 126 MB L2",
+                   "parallelism": f"dp{world}", "dropout": 0.0, "cuda_graph": True, "ms_per_step_eager": ms_eager, "l2": "working set (>20 GB/step) exceeds the 126 MB L2",
                    "loss_last": lossv},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},

@@ -68,16 +68,19 @@ int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E
  * pre_layrnorm, FlaxMBartDecoderLayer, layernorm_embedding, layer_norm [E2,E5,D5,D6]. x,y bf16 [M,d]. */
 int mic_layernorm_fwd(void* stream, const void* x, const float* gamma, const float* beta, float eps, void* y,
                       float* mean, float* rstd, int M, int d);
-int mic_layernorm_bwd_num_partials(void);
-/* dx = dres + LN'(dy); dgamma/dbeta written (=). workspace: 2 * num_partials * d floats */
+/* workspaces (floats) for the two reductions below; `counters`: >= 1024 uint32 that the caller zero-initialises
+ * ONCE - every kernel hands them back zeroed (ticket counters of the "last CTA reduces" scheme). */
+long long mic_layernorm_bwd_workspace_floats(int M, int d);
+long long mic_colsum_workspace_floats(int M, int N);
+/* dx = dres + LN'(dy); dgamma/dbeta written (=) (skipped when dgamma is null) */
 int mic_layernorm_bwd(void* stream, const void* dy, const void* x, const float* gamma, const float* mean,
                       const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, float* workspace,
-                      int M, int d);
-int mic_colsum_num_chunks(int M);
-/* dU = dY * act'(U) (bf16, skipped for MIC_ACT_NONE) and dbias (=|+=) column sums of the result.
- * workspace: mic_colsum_num_chunks(M) * N floats.  Backward of Dense bias + ACT2FN [L2]. */
+                      unsigned int* counters, int M, int d);
+/* dU = dY * act'(U) (bf16, skipped for MIC_ACT_NONE) and dbias (=|+=) column sums of the result (skipped when
+ * dbias is null).  Backward of Dense bias + ACT2FN [L2]. */
 int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act, void* dU,
-                       long long lddu, float* dbias, int accumulate, float* workspace, int M, int N);
+                       long long lddu, float* dbias, int accumulate, float* workspace, unsigned int* counters, int M,
+                       int N);
 /* FlaxMBartDecoder embedding [D1]: shared[id]*scale + embed_positions[pos+offset] -> emb -> layernorm_embedding.
  * pos_ids null -> position = row % pos_mod (arange(T), modeling_clip_vision_mbart.py:490-494). */
 int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids, int pos_mod, int pos_offset,

@@ -25,10 +25,10 @@ SIGNATURES = {
     "mic_lm_head_ce_grad": [P, P, L, P, L, P, P, P, P, F, F, I, I, I, P, L],
     "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P],
     "mic_layernorm_fwd": [P, P, P, P, F, P, P, P, I, I],
-    "mic_layernorm_bwd_num_partials": [],
-    "mic_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I],
-    "mic_colsum_num_chunks": [I],
-    "mic_act_bwd_colsum": [P, P, L, P, L, I, P, L, P, I, P, I, I],
+    "mic_layernorm_bwd_workspace_floats": [I, I],
+    "mic_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I],
+    "mic_colsum_workspace_floats": [I, I],
+    "mic_act_bwd_colsum": [P, P, L, P, L, I, P, L, P, I, P, P, I, I],
     "mic_embed_ln_fwd": [P, P, P, I, I, P, P, F, P, P, F, P, P, P, P, I, I],
     "mic_embed_bwd": [P, P, P, F, P, P, I, I, I],
     "mic_batch_sum": [P, P, I, I, I, P, L],
@@ -80,7 +80,7 @@ def lib() -> C.CDLL:
     for name, args in SIGNATURES.items():
         fn = getattr(l, name)       # AttributeError if the symbol is not exported -> loud
         fn.argtypes = args
-        fn.restype = I
+        fn.restype = L if name.endswith("_workspace_floats") else I
     l.mic_last_error.argtypes = []
     l.mic_last_error.restype = C.c_char_p
     if l.mic_abi_version() != 1:

@@ -37,6 +37,22 @@ __device__ __forceinline__ void frag_b(const bf16* s, int n0, int k0, int lane, 
   b[1] = *reinterpret_cast<const uint32_t*>(s + (n0 + g) * LDS + k0 + 2 * t + 8);
 }
 
+// B fragment (k16 x n8) from a ROW-MAJOR tile M[k][n] (n contiguous) via ldmatrix.trans: no transposed copy needed
+__device__ __forceinline__ void frag_b_trans(const bf16* s, int k0, int n0, int lane, uint32_t* b) {
+  const bf16* row = s + (k0 + (lane & 15)) * LDS + n0;
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(addr));
+}
+// A fragment (m16 x k16) of the TRANSPOSE of a row-major tile M[k][m]: A[m][k] = M[k][m]
+__device__ __forceinline__ void frag_a_trans(const bf16* s, int m0, int k0, int lane, uint32_t* a) {
+  const int i = lane & 7, sel = lane >> 3;     // matrices: 0:(k0,m0) 1:(k0,m0+8) 2:(k0+8,m0) 3:(k0+8,m0+8)
+  const bf16* row = s + (k0 + i + (sel >> 1) * 8) * LDS + m0 + (sel & 1) * 8;
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(addr));
+}
+
 struct AttnArgs {
   const bf16 *Q, *K, *V;
   long long ldq, ldk, ldv;
@@ -53,18 +69,13 @@ struct AttnArgs {
   long long lddq, lddk, lddv;
 };
 
-// load a [rows x 64] head slice into smem (zero-filled beyond `rows`); optionally also its transpose
-__device__ __forceinline__ void load_tile(const bf16* g, long long ld, int rows, bf16* s, bf16* st, int tid, int nthreads) {
+// load a [rows x 64] head slice into smem, row-major, zero-filled beyond `rows` (16-byte vectors, conflict-free)
+__device__ __forceinline__ void load_tile(const bf16* g, long long ld, int rows, bf16* s, int tid, int nthreads) {
   for (int i = tid; i < TMAX * (HD / 8); i += nthreads) {
     const int r = i >> 3, c = (i & 7) * 8;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (r < rows) u = *reinterpret_cast<const uint4*>(g + (long long)r * ld + c);
-    if (s) *reinterpret_cast<uint4*>(s + r * LDS + c) = u;
-    if (st) {
-      const bf16* e = reinterpret_cast<const bf16*>(&u);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) st[(c + j) * LDS + r] = e[j];
-    }
+    *reinterpret_cast<uint4*>(s + r * LDS + c) = u;
   }
 }
 
@@ -79,13 +90,13 @@ __device__ __forceinline__ bool key_allowed(int row, int col, int Tk, int causal
 __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnArgs a) {
   __shared__ __align__(16) bf16 sQ[TMAX * LDS];
   __shared__ __align__(16) bf16 sK[TMAX * LDS];
-  __shared__ __align__(16) bf16 sVt[TMAX * LDS];
+  __shared__ __align__(16) bf16 sV[TMAX * LDS];
   __shared__ int sMask[TMAX];
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  load_tile(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, a.Tq, sQ, nullptr, tid, 128);
-  load_tile(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, a.Tk, sK, nullptr, tid, 128);
-  load_tile(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, a.Tk, nullptr, sVt, tid, 128);
+  load_tile(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, a.Tq, sQ, tid, 128);
+  load_tile(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, a.Tk, sK, tid, 128);
+  load_tile(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, a.Tk, sV, tid, 128);
   if (tid < TMAX) sMask[tid] = (a.key_mask && tid < a.Tk) ? a.key_mask[(long long)b * a.Tk + tid] : 1;
   __syncthreads();
   const int r0 = warp * 16;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnArgs a) {
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) {
       uint32_t bfr[2];
-      frag_b(sVt, nd * 8, kk * 16, lane, bfr);
+      frag_b_trans(sV, kk * 16, nd * 8, lane, bfr);
       mma_bf16_16816(o[nd], af, bfr);
     }
   }
@@ -174,38 +185,37 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnArgs a) {
 // backward: recompute P from Q,K and the saved log-sum-exp; dV = P^T dO ; dP = dO V^T ;
 // dS = scale * P o (dP - rowsum(dO o O)) ; dQ = dS K ; dK = dS^T Q
 // ---------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = (9 * TMAX * LDS) * 2 + TMAX * 4 * 2;
+constexpr int BWD_SMEM = (6 * TMAX * LDS) * 2 + TMAX * 4 * 2;
 
 __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sQt = sQ + TMAX * LDS;
-  bf16* sK = sQt + TMAX * LDS;
-  bf16* sKt = sK + TMAX * LDS;
-  bf16* sV = sKt + TMAX * LDS;
+  bf16* sK = sQ + TMAX * LDS;
+  bf16* sV = sK + TMAX * LDS;
   bf16* sdO = sV + TMAX * LDS;
-  bf16* sdOt = sdO + TMAX * LDS;
-  bf16* sPt = sdOt + TMAX * LDS;
-  bf16* sdSt = sPt + TMAX * LDS;
-  float* sD = reinterpret_cast<float*>(sdSt + TMAX * LDS);
+  bf16* sP = sdO + TMAX * LDS;       // [q][key]
+  bf16* sdS = sP + TMAX * LDS;       // [q][key]
+  float* sD = reinterpret_cast<float*>(sdS + TMAX * LDS);
   int* sMask = reinterpret_cast<int*>(sD + TMAX);
 
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bf16* gQ = a.Q + ((long long)b * a.Tq) * a.ldq + h * HD;
   const bf16* gdO = a.dO + ((long long)b * a.Tq) * a.lddo + h * HD;
   const bf16* gO = a.O + ((long long)b * a.Tq) * a.ldo + h * HD;
-  load_tile(gQ, a.ldq, a.Tq, sQ, sQt, tid, 128);
-  load_tile(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, a.Tk, sK, sKt, tid, 128);
-  load_tile(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, a.Tk, sV, nullptr, tid, 128);
-  load_tile(gdO, a.lddo, a.Tq, sdO, sdOt, tid, 128);
+  load_tile(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, a.Tq, sQ, tid, 128);
+  load_tile(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, a.Tk, sK, tid, 128);
+  load_tile(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, a.Tk, sV, tid, 128);
+  load_tile(gdO, a.lddo, a.Tq, sdO, tid, 128);
   if (tid < TMAX) sMask[tid] = (a.key_mask && tid < a.Tk) ? a.key_mask[(long long)b * a.Tk + tid] : 1;
-  if (tid < TMAX) {
+  {
+    // D[q] = sum_d dO[q][d] * O[q][d] : two threads per row
+    const int r = tid >> 1, hf = tid & 1;
     float d = 0.f;
-    if (tid < a.Tq) {
-      for (int c = 0; c < HD; c += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(gdO + (long long)tid * a.lddo + c);
-        const uint4 w = *reinterpret_cast<const uint4*>(gO + (long long)tid * a.ldo + c);
+    if (r < a.Tq) {
+#pragma unroll
+      for (int c = hf * 32; c < hf * 32 + 32; c += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(gdO + (long long)r * a.lddo + c);
+        const uint4 w = *reinterpret_cast<const uint4*>(gO + (long long)r * a.ldo + c);
         const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
         const uint32_t* ww = reinterpret_cast<const uint32_t*>(&w);
 #pragma unroll
@@ -215,7 +225,8 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
         }
       }
     }
-    sD[tid] = d;
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    if (hf == 0) sD[r] = d;
   }
   __syncthreads();
 
@@ -251,22 +262,29 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
       lse[i] = row < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + row] : 0.f;
       dd[i] = sD[row];
     }
-    // P and dS (in place: s <- P, dp <- dS), stash transposes for the key-side contractions
+    // P and dS (in place: s <- P, dp <- dS); stash both row-major for the key-side contractions
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = j >> 1;
-        const int row = r0 + g + i * 8, col = nt * 8 + 2 * t + (j & 1);
-        const bool ok = row < a.Tq && key_allowed(row, col, a.Tk, a.causal, a.key_mask ? sMask : nullptr);
-        const float p = ok ? __expf(s[nt][j] * a.scale - lse[i]) : 0.f;
-        const float ds = p * (dp[nt][j] - dd[i]) * a.scale;
-        s[nt][j] = p;
-        dp[nt][j] = ds;
-        sPt[col * LDS + row] = __float2bfloat16_rn(p);
-        sdSt[col * LDS + row] = __float2bfloat16_rn(ds);
+      for (int i = 0; i < 2; ++i) {
+        const int row = r0 + g + i * 8;
+        float pv[2], dsv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = i * 2 + e, col = nt * 8 + 2 * t + e;
+          const bool ok = row < a.Tq && key_allowed(row, col, a.Tk, a.causal, a.key_mask ? sMask : nullptr);
+          const float p = ok ? __expf(s[nt][j] * a.scale - lse[i]) : 0.f;
+          const float ds = p * (dp[nt][j] - dd[i]) * a.scale;
+          s[nt][j] = p;
+          dp[nt][j] = ds;
+          pv[e] = p;
+          dsv[e] = ds;
+        }
+        *reinterpret_cast<uint32_t*>(sP + row * LDS + nt * 8 + 2 * t) = pack_bf16(pv[0], pv[1]);
+        *reinterpret_cast<uint32_t*>(sdS + row * LDS + nt * 8 + 2 * t) = pack_bf16(dsv[0], dsv[1]);
       }
-    // dQ = dS K
+    }
+    // dQ = dS K   (B: n = d, k = key -> row-major sK through ldmatrix.trans)
     float dq[8][4];
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd)
@@ -282,7 +300,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd) {
         uint32_t bfr[2];
-        frag_b(sKt, nd * 8, kk * 16, lane, bfr);
+        frag_b_trans(sK, kk * 16, nd * 8, lane, bfr);
         mma_bf16_16816(dq[nd], af, bfr);
       }
     }
@@ -298,7 +316,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
     }
   }
   __syncthreads();
-  // key side: this warp owns keys [r0, r0+16)
+  // key side: this warp owns keys [r0, r0+16):  dV = P^T dO,  dK = dS^T Q
   if (r0 < a.Tk) {
     float dv[8][4], dk[8][4];
 #pragma unroll
@@ -311,13 +329,13 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) {
       uint32_t ap[4], ads[4];
-      frag_a(sPt, r0, qq * 16, lane, ap);
-      frag_a(sdSt, r0, qq * 16, lane, ads);
+      frag_a_trans(sP, r0, qq * 16, lane, ap);
+      frag_a_trans(sdS, r0, qq * 16, lane, ads);
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd) {
         uint32_t bdo[2], bq[2];
-        frag_b(sdOt, nd * 8, qq * 16, lane, bdo);
-        frag_b(sQt, nd * 8, qq * 16, lane, bq);
+        frag_b_trans(sdO, qq * 16, nd * 8, lane, bdo);
+        frag_b_trans(sQ, qq * 16, nd * 8, lane, bq);
         mma_bf16_16816(dv[nd], ap, bdo);
         mma_bf16_16816(dk[nd], ads, bq);
       }

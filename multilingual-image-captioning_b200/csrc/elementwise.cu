@@ -85,105 +85,146 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm backward.  Persistent blocks stride over rows; per-thread dgamma/dbeta partials are
-// reduced across the block's warps in shared memory and written to partial[block][d].
-//   dx = dres + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))
+// LayerNorm backward, two kernels:
+//  (1) dx = dres + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))   one warp per row, lean registers
+//  (2) dgamma = sum_rows dy*xhat, dbeta = sum_rows dy : column-parallel over row chunks; the last CTA of a
+//      column block (atomic ticket) folds the per-chunk partials, so no follow-up reduction launch.
 // ---------------------------------------------------------------------------------------------
-constexpr int LNB_WARPS = 8;
-__global__ void __launch_bounds__(LNB_WARPS * 32)
-layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
-                     bf16* __restrict__ dx, float* __restrict__ part_dg, float* __restrict__ part_db, int M, int d) {
-  __shared__ float red[LNB_WARPS][1024];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dg[LN_MAX_ITERS][8], db[LN_MAX_ITERS][8], g[LN_MAX_ITERS][8];
+__global__ void __launch_bounds__(256)
+layernorm_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
+                        bf16* __restrict__ dx, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float mu = mean[row], rs = rstd[row];
+  float dyg[LN_MAX_ITERS][8], xh[LN_MAX_ITERS][8];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int it = 0; it < LN_MAX_ITERS; ++it) {
     const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float g[8];
+      load8(dy + (long long)row * d + c, dyg[it]);
+      load8(x + (long long)row * d + c, xh[it]);
+      load8f(gamma + c, g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dg[it][j] = 0.f;
-      db[it][j] = 0.f;
-      g[it][j] = 0.f;
-    }
-    if (c < d) load8f(gamma + c, g[it]);
-  }
-  for (int row = blockIdx.x * LNB_WARPS + warp; row < M; row += gridDim.x * LNB_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    float dyv[LN_MAX_ITERS][8], xh[LN_MAX_ITERS][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int it = 0; it < LN_MAX_ITERS; ++it) {
-      const int c = lane * 8 + it * 256;
-      if (c < d) {
-        load8(dy + (long long)row * d + c, dyv[it]);
-        load8(x + (long long)row * d + c, xh[it]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[it][j] = (xh[it][j] - mu) * rs;
-          const float t = dyv[it][j] * g[it][j];
-          s1 += t;
-          s2 += t * xh[it][j];
-          dg[it][j] += dyv[it][j] * xh[it][j];
-          db[it][j] += dyv[it][j];
-        }
-      }
-    }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
-#pragma unroll
-    for (int it = 0; it < LN_MAX_ITERS; ++it) {
-      const int c = lane * 8 + it * 256;
-      if (c < d) {
-        float o[8], r[8];
-        if (dres) load8(dres + (long long)row * d + c, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (dyv[it][j] * g[it][j] - s1 - xh[it][j] * s2);
-          if (dres) o[j] += r[j];
-        }
-        store8(dx + (long long)row * d + c, o);
+      for (int j = 0; j < 8; ++j) {
+        xh[it][j] = (xh[it][j] - mu) * rs;
+        dyg[it][j] *= g[j];
+        s1 += dyg[it][j];
+        s2 = fmaf(dyg[it][j], xh[it][j], s2);
       }
     }
   }
-  // block reduce dgamma then dbeta
-  for (int pass = 0; pass < 2; ++pass) {
+  s1 = warp_sum(s1) / d;
+  s2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int it = 0; it < LN_MAX_ITERS; ++it) {
-      const int c = lane * 8 + it * 256;
-      if (c < d) {
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float o[8], r[8];
+      if (dres) load8(dres + (long long)row * d + c, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp][c + j] = pass == 0 ? dg[it][j] : db[it][j];
+      for (int j = 0; j < 8; ++j) {
+        o[j] = rs * (dyg[it][j] - s1 - xh[it][j] * s2);
+        if (dres) o[j] += r[j];
       }
+      store8(dx + (long long)row * d + c, o);
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < LNB_WARPS; ++w) s += red[w][c];
-      (pass == 0 ? part_dg : part_db)[(long long)blockIdx.x * d + c] = s;
-    }
-    __syncthreads();
   }
 }
 
-// out[c] (=|+=) sum_p part[p][c]
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out,
-                                       int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(long long)p * n + c];
-  out[c] = accumulate ? out[c] + s : s;
+// "last CTA reduces": after writing its partial row, a CTA takes a ticket; the CTA that draws the last
+// ticket of its column block sums all partials of that block and resets the counter for the next launch.
+__device__ __forceinline__ bool last_cta_of_column(unsigned int* counter, unsigned int total) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == total - 1);
+    if (is_last) *counter = 0;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// grid = (ceil(d/256), chunks); block 256 = 32 column groups (8 cols) x 8 row lanes
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, float* __restrict__ part, unsigned int* __restrict__ counters,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d, int rows_per_chunk) {
+  __shared__ float red[8][2][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  float ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ag[j] = 0.f;
+    ab[j] = 0.f;
+  }
+  if (c < d) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float g[8], xv[8];
+      load8(dy + (long long)r * d + c, g);
+      load8(x + (long long)r * d + c, xv);
+      const float mu = mean[r], rs = rstd[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ag[j] = fmaf(g[j], (xv[j] - mu) * rs, ag[j]);
+        ab[j] += g[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[rl][0][cg * 8 + j] = ag[j];
+    red[rl][1][cg * 8 + j] = ab[j];
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int col = blockIdx.x * 256 + t;
+  const int nch = gridDim.y;
+  if (col < d) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      sg += red[w][0][t];
+      sb += red[w][1][t];
+    }
+    part[((long long)blockIdx.y * 2 + 0) * d + col] = sg;
+    part[((long long)blockIdx.y * 2 + 1) * d + col] = sb;
+  }
+  if (last_cta_of_column(counters + blockIdx.x, nch) && col < d) {
+    float sg0 = 0.f, sg1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+    int p = 0;
+    for (; p + 1 < nch; p += 2) {
+      sg0 += part[((long long)p * 2 + 0) * d + col];
+      sb0 += part[((long long)p * 2 + 1) * d + col];
+      sg1 += part[((long long)p * 2 + 2) * d + col];
+      sb1 += part[((long long)p * 2 + 3) * d + col];
+    }
+    if (p < nch) {
+      sg0 += part[((long long)p * 2 + 0) * d + col];
+      sb0 += part[((long long)p * 2 + 1) * d + col];
+    }
+    dgamma[col] = sg0 + sg1;
+    dbeta[col] = sb0 + sb1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// dU = dY * act'(U)  (optional) and column sums of the result (bias gradient), two-stage.
+// dU = dY * act'(U)  (optional) and column sums of the result (bias gradient), same last-CTA scheme.
 // block = 32 column-groups (8 cols each) x 8 row lanes; grid = (ceil(N/256), row_chunks)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __restrict__ U, long long ldu, int act,
-                      bf16* __restrict__ dU, long long lddu, float* __restrict__ part, int M, int N,
+                      bf16* __restrict__ dU, long long lddu, float* __restrict__ part,
+                      unsigned int* __restrict__ counters, float* __restrict__ dbias, int accumulate, int M, int N,
                       int rows_per_chunk) {
   __shared__ float red[8][256 + 8];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -208,15 +249,28 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __
       for (int j = 0; j < 8; ++j) acc[j] += g[j];
     }
   }
+  if (!dbias) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
   __syncthreads();
   const int t = threadIdx.x;
-  if (part && blockIdx.x * 256 + t < N) {
+  const int col = blockIdx.x * 256 + t;
+  const int nch = gridDim.y;
+  if (col < N) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][t];
-    part[(long long)blockIdx.y * N + blockIdx.x * 256 + t] = s;
+    part[(long long)blockIdx.y * N + col] = s;
+  }
+  if (last_cta_of_column(counters + blockIdx.x, nch) && col < N) {
+    float s0 = 0.f, s1 = 0.f;
+    int p = 0;
+    for (; p + 1 < nch; p += 2) {
+      s0 += part[(long long)p * N + col];
+      s1 += part[(long long)(p + 1) * N + col];
+    }
+    if (p < nch) s0 += part[(long long)p * N + col];
+    dbias[col] = accumulate ? dbias[col] + s0 + s1 : s0 + s1;
   }
 }
 
@@ -540,47 +594,54 @@ extern "C" int mic_layernorm_fwd(void* stream, const void* x, const float* gamma
   return MIC_OK;
 }
 
-extern "C" int mic_layernorm_bwd_num_partials(void) { return mic_num_sms() * 2; }
-
-extern "C" int mic_layernorm_bwd(void* stream, const void* dy, const void* x, const float* gamma, const float* mean,
-                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                                 float* workspace, int M, int d) {
-  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm_bwd: d=%d must be a multiple of 8 and <= 1024", d);
-  int nb = mic_layernorm_bwd_num_partials();
-  const int need = (M + LNB_WARPS - 1) / LNB_WARPS;
-  if (nb > need) nb = need;
-  float* pg = workspace;
-  float* pb = workspace + (long long)nb * d;
-  layernorm_bwd_kernel<<<nb, LNB_WARPS * 32, 0, STREAM>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
-                                                          (const bf16*)dres, (bf16*)dx, pg, pb, M, d);
-  MIC_CHECK_LAUNCH();
-  reduce_partials_kernel<<<(d + 255) / 256, 256, 0, STREAM>>>(pg, nb, d, dgamma, 0);
-  reduce_partials_kernel<<<(d + 255) / 256, 256, 0, STREAM>>>(pb, nb, d, dbeta, 0);
-  MIC_CHECK_LAUNCH();
-  return MIC_OK;
-}
-
-extern "C" int mic_colsum_num_chunks(int M) {
-  int chunks = (M + 255) / 256;
-  if (chunks > 64) chunks = 64;
+static int pick_chunks(int M, int col_blocks) {
+  int chunks = (2 * mic_num_sms() + col_blocks - 1) / col_blocks;
+  const int by_rows = (M + 511) / 512;                    // at most 512 rows (64 iterations per thread) per chunk
+  if (chunks < by_rows) chunks = by_rows;
+  const int max_chunks = (M + 31) / 32;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 256) chunks = 256;
   return chunks < 1 ? 1 : chunks;
 }
 
-extern "C" int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act,
-                                  void* dU, long long lddu, float* dbias, int accumulate, float* workspace, int M,
-                                  int N) {
-  MIC_CHECK_ARG(N % 8 == 0 && ldy % 8 == 0, "act_bwd_colsum: N and ld must be multiples of 8");
-  MIC_CHECK_ARG(act == MIC_ACT_NONE || (U && dU), "act_bwd_colsum: activation backward needs U and dU");
-  const int chunks = mic_colsum_num_chunks(M);
-  const int rows_per_chunk = (M + chunks - 1) / chunks;
-  dim3 grid((N + 255) / 256, chunks);
-  act_bwd_colsum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)dY, ldy, (const bf16*)U, ldu, act, (bf16*)dU, lddu,
-                                                  dbias ? workspace : nullptr, M, N, rows_per_chunk);
+// workspace sizes in floats (partials).  `counters`: >= 1024 uint32, zero-initialised ONCE by the caller;
+// every kernel leaves them zero again.
+extern "C" long long mic_layernorm_bwd_workspace_floats(int M, int d) {
+  return 2ll * pick_chunks(M, (d + 255) / 256) * d;
+}
+extern "C" long long mic_colsum_workspace_floats(int M, int N) { return (long long)pick_chunks(M, (N + 255) / 256) * N; }
+
+extern "C" int mic_layernorm_bwd(void* stream, const void* dy, const void* x, const float* gamma, const float* mean,
+                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 float* workspace, unsigned int* counters, int M, int d) {
+  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm_bwd: d=%d must be a multiple of 8 and <= 1024", d);
+  layernorm_bwd_dx_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
+                                                           (const bf16*)dres, (bf16*)dx, M, d);
   MIC_CHECK_LAUNCH();
-  if (dbias) {
-    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, STREAM>>>(workspace, chunks, N, dbias, accumulate);
+  if (dgamma) {
+    const int cb = (d + 255) / 256;
+    const int chunks = pick_chunks(M, cb);
+    dim3 grid(cb, chunks);
+    ln_param_grad_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)dy, (const bf16*)x, mean, rstd, workspace, counters,
+                                                   dgamma, dbeta, M, d, (M + chunks - 1) / chunks);
     MIC_CHECK_LAUNCH();
   }
+  return MIC_OK;
+}
+
+extern "C" int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act,
+                                  void* dU, long long lddu, float* dbias, int accumulate, float* workspace,
+                                  unsigned int* counters, int M, int N) {
+  MIC_CHECK_ARG(N % 8 == 0 && ldy % 8 == 0, "act_bwd_colsum: N and ld must be multiples of 8");
+  MIC_CHECK_ARG(act == MIC_ACT_NONE || (U && dU), "act_bwd_colsum: activation backward needs U and dU");
+  const int cb = (N + 255) / 256;
+  MIC_CHECK_ARG(cb <= 1024, "act_bwd_colsum: N=%d too wide for the counter array", N);
+  const int chunks = pick_chunks(M, cb);
+  dim3 grid(cb, chunks);
+  act_bwd_colsum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)dY, ldy, (const bf16*)U, ldu, act, (bf16*)dU, lddu,
+                                                  workspace, counters, dbias, accumulate, M, N,
+                                                  (M + chunks - 1) / chunks);
+  MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
 

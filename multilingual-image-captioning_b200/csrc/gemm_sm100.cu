@@ -69,8 +69,10 @@ int mic_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t
 // ------------------------------------------------------------------------------------------------
 using namespace micgemm;
 
-static int pick_block_n(int M, int N, int forced) {
+static int pick_block_n(int M, int N, int forced, bool splittable = false) {
   if (forced == 128 || forced == 192 || forced == 256) return forced;
+  // fp32 wgrad-style outputs can be split along K to fill the machine, so keep the efficient wide tile
+  if (splittable && N > 128) return (N % 256 != 0 && N % 192 == 0) ? 192 : 256;
   const int sms = mic_num_sms();
   const int mb = (M + BLOCK_M - 1) / BLOCK_M;
   int best = 256;
@@ -99,11 +101,11 @@ struct Operands {
 };
 
 static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb,
-                          int M, int N, int K, int block_n, int group_m) {
+                          int M, int N, int K, int block_n, int group_m, bool splittable = false) {
   MIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
   memset(&o->td, 0, sizeof(CUtensorMap));
   memset(&o->td2, 0, sizeof(CUtensorMap));
-  o->bn = pick_block_n(M, N, block_n);
+  o->bn = pick_block_n(M, N, block_n, splittable);
   int rc;
   if (!a_mn)
     rc = mic_make_tmap_bf16_2d(&o->ta, A, K, M, lda, BLOCK_K, BLOCK_M);
@@ -158,7 +160,10 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
                              int accumulate, const float* bias, int act, void* D2, const void* residual,
                              long long ldr, int block_n, int group_m, int split_k) {
   Operands o;
-  int rc = setup_operands(&o, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, block_n, group_m);
+  const bool splittable = d_is_f32 && !bias && act == MIC_ACT_NONE && !D2 && !residual && split_k != 1 &&
+                          ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((ldd * 4) % 16 == 0) && (N % 8 == 0) &&
+                          K >= 2048;
+  int rc = setup_operands(&o, a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, block_n, group_m, splittable);
   if (rc) return rc;
   MIC_CHECK_ARG(D != nullptr, "null output");
   MIC_CHECK_ARG(!(accumulate && !d_is_f32), "accumulate requires fp32 output");

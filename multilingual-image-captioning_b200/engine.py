@@ -66,7 +66,7 @@ class CaptionEngine:
     def _ln_bwd(self, dy, x, name, stats, dres, dx):
         ps = self.ps
         d = x.shape[1]
-        ws = self._workspace(max(ops.ln_bwd_workspace_floats(d), 1))
+        ws = self._workspace(max(ops.ln_bwd_workspace_floats(x.shape[0], d), 1))
         ops.layernorm_bwd(dy, x, ps.f(name + ".scale"), stats[0], stats[1], dres, dx, ps.g(name + ".scale"),
                           ps.g(name + ".bias"), ws)
         return dx

@@ -95,18 +95,16 @@ def _forced_token(cur_len, max_length, forced_bos, forced_eos):
     return f
 
 
-@torch.no_grad()
-def generate(engine, pixel_values, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams,
-             min_length, forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping):
-    """`generate` :128-336.  encode() truncates pixels to int32 first (modeling_clip_vision_mbart.py:330)."""
+def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams, min_length,
+                 forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping):
+    """Enqueue encode + the whole search loop on the current stream (no host synchronisation inside:
+    the while_loop condition lives in the device flag `active`).  Capturable into one CUDA graph."""
     t, ps = engine.t, engine.ps
     dev = engine.dev
-    B = pixel_values.shape[0]
+    B = px.shape[0]
     K, Lmax, V = num_beams, max_length, t.vocab_size
-    if K > 4:
-        raise NotImplementedError("beam-step kernel keeps 2*num_beams <= 8 candidates (num_beams <= 4)")
     R = B * K
-    enc = engine.encode(pixel_values, trunc_int=True, save=False, tag="gen.enc")
+    enc = engine.encode(px, trunc_int=True, save=False, tag="gen.enc")
     enc_kv = engine.cross_kv(enc, tag="gen.enc")
     cache = DecodeCache(engine, R, Lmax, enc_kv, K, use_ancestors=K > 1)
     ws = _search_ws(engine, R)
@@ -133,11 +131,12 @@ def generate(engine, pixel_values, *, max_length, pad_token_id, eos_token_id, de
 
     st = {"running_seq": torch.full((B, K, Lmax), pad_token_id, dtype=I32, device=dev),
           "sequences": torch.full((B, K, Lmax), pad_token_id, dtype=I32, device=dev),
-          "running_scores": torch.tensor([0.0] + [-1.0e7] * (K - 1), dtype=F32, device=dev).repeat(B, 1).contiguous(),
+          "running_scores": torch.full((B, K), -1.0e7, dtype=F32, device=dev),     # [0, -1e7, ...] set below
           "scores": torch.full((B, K), -1.0e7, dtype=F32, device=dev),
           "finished": torch.zeros((B, K), dtype=I32, device=dev),
           "ancestors": cache.ancestors, "next_token": next_token, "active": active}
     st["running_seq"][:, :, 0] = decoder_start_token_id
+    st["running_scores"][:, 0] = 0.0
     for cur_len in range(1, Lmax):
         forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
         last = cur_len == Lmax - 1
@@ -153,3 +152,32 @@ def generate(engine, pixel_values, *, max_length, pad_token_id, eos_token_id, de
     out_scores = torch.empty((B,), dtype=F32, device=dev)
     ops.beam_finalize(st, B, K, Lmax, out_seq, out_scores)
     return {"sequences": out_seq, "scores": out_scores}
+
+
+@torch.no_grad()
+def generate(engine, pixel_values, *, use_cuda_graph=True, **kw):
+    """`generate` :128-336.  encode() truncates pixels to int32 first (modeling_clip_vision_mbart.py:330).
+    The first call for a given (batch, search settings) runs eagerly (allocates every buffer); the whole
+    loop is then captured into ONE CUDA graph and later calls only copy the pixels in and replay it."""
+    if kw["num_beams"] > 4:
+        raise NotImplementedError("beam-step kernel keeps 2*num_beams <= 8 candidates (num_beams <= 4)")
+    px = pixel_values.to(engine.dev, F32).contiguous()
+    if not use_cuda_graph:
+        return _search_loop(engine, px, **kw)
+    key = (tuple(px.shape),) + tuple(sorted(kw.items()))
+    graphs = engine.__dict__.setdefault("_gen_graphs", {})
+    entry = graphs.get(key)
+    if entry is None:
+        static_px = px.clone()
+        out = _search_loop(engine, static_px, **kw)          # eager warm-up: result of this call
+        result = {k: v.clone() for k, v in out.items()}
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gout = _search_loop(engine, static_px, **kw)
+        graphs[key] = (g, static_px, gout)
+        return result
+    g, static_px, gout = entry
+    static_px.copy_(px)
+    g.replay()
+    return {k: v.clone() for k, v in gout.items()}

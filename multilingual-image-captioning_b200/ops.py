@@ -125,25 +125,39 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, mean=None, rstd=None):
     return out
 
 
-def ln_bwd_workspace_floats(d):
-    return 2 * lib().mic_layernorm_bwd_num_partials() * d
+_COUNTERS = {}
+
+
+def counters(device):
+    """Ticket counters of the 'last CTA reduces' kernels: zero-initialised once per device, kernels reset them."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    c = _COUNTERS.get(key)
+    if c is None:
+        c = torch.zeros(1024, dtype=torch.int32, device=dev)
+        _COUNTERS[key] = c
+    return c
+
+
+def ln_bwd_workspace_floats(M, d):
+    return lib().mic_layernorm_bwd_workspace_floats(M, d)
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, workspace):
     M, d = x.shape
     _call("mic_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dgamma),
-          _p(dbeta), _p(workspace), M, d)
+          _p(dbeta), _p(workspace), _p(counters(x.device)), M, d)
     return dx
 
 
 def colsum_workspace_floats(M, N):
-    return lib().mic_colsum_num_chunks(M) * N
+    return lib().mic_colsum_workspace_floats(M, N)
 
 
 def act_bwd_colsum(dy, u, act, du, dbias, workspace, accumulate=False):
     M, N = dy.shape
     _call("mic_act_bwd_colsum", _p(dy), _ld(dy), _p(u), _ld(u) if u is not None else 0, ACT[act], _p(du),
-          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), M, N)
+          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), _p(counters(dy.device)), M, N)
 
 
 def embed_ln_fwd(ids, pos_ids, pos_mod, pos_offset, table, pos_table, scale, gamma, beta, eps, emb, out,

@@ -98,16 +98,51 @@ class TrainState:
         return lr
 
 
+def _static_batch(state, batch):
+    """Persistent device buffers for the step inputs (so the captured graph sees fixed addresses)."""
+    dev = state.store.device
+    px = torch.as_tensor(batch["pixel_values"])
+    key = (tuple(px.shape), tuple(torch.as_tensor(batch["decoder_input_ids"]).shape))
+    sb = state.__dict__.get("_static")
+    if sb is None or sb["key"] != key:
+        B, T = key[1]
+        sb = {"key": key, "graph": None,
+              "pixel_values": torch.empty(key[0], dtype=F32, device=dev),
+              "decoder_input_ids": torch.empty((B, T), dtype=torch.int32, device=dev),
+              "attention_mask": torch.empty((B, T), dtype=torch.int32, device=dev),
+              "input_ids": torch.empty((B, T), dtype=torch.int32, device=dev)}
+        state._static = sb
+    for k in ("pixel_values", "decoder_input_ids", "attention_mask", "input_ids"):
+        sb[k].copy_(torch.as_tensor(batch[k]), non_blocking=True)
+    return sb
+
+
 @torch.no_grad()
-def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0):
+def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, use_cuda_graph: bool = True):
     """One optimisation step.  batch keys as the reference's collate output (main.py:493-523):
     pixel_values (B,H,W,3) f32, input_ids = labels (B,T), attention_mask (B,T), decoder_input_ids (B,T).
-    Returns (state, metrics) with metrics = {"loss": 0-d tensor, "learning_rate": float}."""
+    Returns (state, metrics) with metrics = {"loss": 0-d tensor, "learning_rate": float}.
+
+    The forward+backward kernel sequence is shape-static, so after one eager step it is captured into a
+    CUDA graph and replayed (no per-kernel host launch cost); the NCCL all-reduce and AdamW stay outside."""
     eng = state.model.engine
-    dev = state.store.device
-    ws = eng.forward_backward(torch.as_tensor(batch["pixel_values"]).to(dev), torch.as_tensor(batch["decoder_input_ids"]),
-                              torch.as_tensor(batch["attention_mask"]), torch.as_tensor(batch["input_ids"]),
-                              label_smoothing=label_smoothing_factor)
+    sb = _static_batch(state, batch)
+    args = (sb["pixel_values"], sb["decoder_input_ids"], sb["attention_mask"], sb["input_ids"])
+    if not use_cuda_graph:
+        ws = eng.forward_backward(*args, label_smoothing=label_smoothing_factor)
+    elif sb["graph"] is None or sb.get("ls") != label_smoothing_factor:
+        ws = eng.forward_backward(*args, label_smoothing=label_smoothing_factor)      # eager: allocates all buffers
+        if sb.get("warm"):
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ws = eng.forward_backward(*args, label_smoothing=label_smoothing_factor)
+            sb["graph"], sb["ws"], sb["ls"] = g, ws, label_smoothing_factor
+            g.replay()
+        sb["warm"] = True
+    else:
+        sb["graph"].replay()
+        ws = sb["ws"]
     state.allreduce_grads()
     lr = state.apply_gradients()
     loss = ws["out"][0:1].clone()

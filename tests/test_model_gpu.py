@@ -181,3 +181,21 @@ def test_cached_decode_api_matches_full_forward():
         cache = step.past_key_values
     with pytest.raises(ValueError):
         model.decode(ids[:, :1], enc, past_key_values=cache)
+
+
+def test_generate_cuda_graph_replay_equals_eager():
+    """Second call replays the captured graph; it must reproduce the eager result and track new pixels."""
+    cfg, params, batch, model = _setup(vocab=1003, layers=2, B=3, std=0.3, seed=5)
+    kw = dict(num_beams=4, max_length=12, forced_bos_token_id=1001)
+    a = model.generate(batch["pixel_values"], **kw)            # eager (captures afterwards)
+    b = model.generate(batch["pixel_values"], **kw)            # replay
+    assert torch.equal(a.sequences, b.sequences) and torch.equal(a.scores, b.scores)
+    other = synthetic.make_batch(cfg, 3, seq_len=16, seed=9)["pixel_values"]
+    c = model.generate(other, **kw)                            # replay with new input
+    ref = rg.generate(params, other, cfg, **kw)
+    assert np.all(c.sequences.cpu().numpy()[:, :2] == ref["sequences"][:, :2])
+    d = model.generate(batch["pixel_values"], **kw)
+    assert torch.equal(a.sequences, d.sequences)
+    g1 = model.generate(batch["pixel_values"], num_beams=1, max_length=12, forced_bos_token_id=1001)
+    g2 = model.generate(batch["pixel_values"], num_beams=1, max_length=12, forced_bos_token_id=1001)
+    assert torch.equal(g1.sequences, g2.sequences)

@@ -147,7 +147,7 @@ def test_layernorm_fwd_bwd(M, d):
     dres = rnd(M, d, seed=22)
     dx = torch.empty_like(x)
     dg, db = torch.empty(d, device=DEV), torch.empty(d, device=DEV)
-    ws = torch.empty(ops.ln_bwd_workspace_floats(d), device=DEV)
+    ws = torch.empty(ops.ln_bwd_workspace_floats(M, d), device=DEV)
     ops.layernorm_bwd(dy, x, gamma, mean, rstd, dres, dx, dg, db, ws)
     want.backward(dy.float())
     torch.cuda.synchronize()
