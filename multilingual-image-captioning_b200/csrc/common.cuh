@@ -99,9 +99,17 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {  // d act / dx
   if (act == MIC_ACT_GELU) {
-    float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-    float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    // d/dx [x Phi(x)] = Phi(x) + x phi(x); erf and the normal pdf share exp(-x^2/2)
+    const float ax = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    p *= t;
+    const float e = exp2f(-ax * ax * 1.4426950408889634f);      // = exp(-x^2/2)
+    const float erfv = copysignf(fmaf(-p, e, 1.0f), x);
+    return fmaf(0.5f, erfv, 0.5f) + x * 0.3989422804014327f * e;
   }
   if (act == MIC_ACT_QUICK_GELU) {
     float s = 1.0f / (1.0f + __expf(-1.702f * x));

@@ -70,7 +70,10 @@ int mic_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t
 using namespace micgemm;
 
 static int pick_block_n(int M, int N, int forced, bool splittable = false) {
-  if (forced == 128 || forced == 192 || forced == 256) return forced;
+  if (forced == 64 || forced == 128 || forced == 192 || forced == 256) return forced;
+  // skinny-M (decode-time) GEMMs are weight streaming: narrow tiles so every weight matrix is pulled by
+  // many SMs at once instead of N/256 of them
+  if (M <= 2 * BLOCK_M && !splittable && N >= 512) return 64;
   // fp32 wgrad-style outputs can be split along K to fill the machine, so keep the efficient wide tile
   if (splittable && N > 128) return (N % 256 != 0 && N % 192 == 0) ? 192 : 256;
   const int sms = mic_num_sms();
@@ -106,6 +109,7 @@ static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long l
   memset(&o->td, 0, sizeof(CUtensorMap));
   memset(&o->td2, 0, sizeof(CUtensorMap));
   o->bn = pick_block_n(M, N, block_n, splittable);
+  if (o->bn == 64 && !(a_mn == 0 && b_mn == 1)) o->bn = 128;
   int rc;
   if (!a_mn)
     rc = mic_make_tmap_bf16_2d(&o->ta, A, K, M, lda, BLOCK_K, BLOCK_M);
@@ -151,6 +155,9 @@ static int launch_bn(cudaStream_t stream, const Operands& o, const typename Epi:
   switch (o.bn) {
     case 256: return launch_one<A_MN, B_MN, 256, Epi>(stream, o, ep);
     case 192: return launch_one<A_MN, B_MN, 192, Epi>(stream, o, ep);
+    case 64:
+      if (A_MN == 0 && B_MN == 1) return launch_one<0, 1, 64, Epi>(stream, o, ep);   // forward layout only
+      return launch_one<A_MN, B_MN, 128, Epi>(stream, o, ep);
     default: return launch_one<A_MN, B_MN, 128, Epi>(stream, o, ep);
   }
 }

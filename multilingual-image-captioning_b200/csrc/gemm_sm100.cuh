@@ -31,11 +31,11 @@ constexpr int STG_BYTES = 4096;         // per-warp staging: 32 rows x 128 B
 
 template <int BN>
 struct Cfg {
-  static_assert(BN == 128 || BN == 192 || BN == 256, "unsupported BLOCK_N");
+  static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported BLOCK_N");
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : 6);
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int EPI_BYTES = NUM_EPI_WARPS * STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int NUM_GROUPS = BN / GROUP_COLS;
@@ -184,14 +184,18 @@ struct EpiStore {
     }
     // ---- optional pre-activation copy ----
     if (p.D2) {
-      stg_acquire(lane);
+      // direct row-per-thread stores: keeps the single staging buffer free for the main output, so the
+      // two outputs of a group never wait on each other's TMA read (the LSU has slack here)
+      if (ctx.row < s.M) {
+        bf16* d2 = p.D2 + (long long)ctx.row * p.ldd + col0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float* x = v + u * 8;
-        *reinterpret_cast<uint4*>(stg_addr(stg, lane, u)) =
-            make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        for (int u = 0; u < 8; ++u) {
+          const float* x = v + u * 8;
+          if (col0 + u * 8 < s.N)
+            *reinterpret_cast<uint4*>(d2 + u * 8) =
+                make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        }
       }
-      stg_store(ctx.tmap_d2, stg, lane, col0, ctx.row0, false);
     }
     if (p.act != MIC_ACT_NONE) {
 #pragma unroll
@@ -625,6 +629,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
         Epi::group(ep, st, shape, ctx, tc.n_blk * BN + g * GROUP_COLS, v);
+      }
+      if (g_begin == g_end) {                        // narrow tiles: this warp owns no column group
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
       }
       Epi::tile_end(ep, st, shape, ctx.row, tc.m_blk, tc.n_blk, half);
     }

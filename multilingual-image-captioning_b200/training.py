@@ -98,22 +98,52 @@ class TrainState:
         return lr
 
 
+_KEYS = ("pixel_values", "decoder_input_ids", "attention_mask", "input_ids")
+
+
 def _static_batch(state, batch):
-    """Persistent device buffers for the step inputs (so the captured graph sees fixed addresses)."""
+    """Persistent device buffers for the step inputs (so the captured graph sees fixed addresses).
+
+    Host batches travel on a dedicated copy stream into one of two landing buffers, so the H2D transfer of
+    step i overlaps the GPU work of step i-1 that is still in flight; the compute stream then takes a cheap
+    device-to-device copy into the static inputs."""
     dev = state.store.device
     px = torch.as_tensor(batch["pixel_values"])
     key = (tuple(px.shape), tuple(torch.as_tensor(batch["decoder_input_ids"]).shape))
     sb = state.__dict__.get("_static")
     if sb is None or sb["key"] != key:
         B, T = key[1]
-        sb = {"key": key, "graph": None,
-              "pixel_values": torch.empty(key[0], dtype=F32, device=dev),
-              "decoder_input_ids": torch.empty((B, T), dtype=torch.int32, device=dev),
-              "attention_mask": torch.empty((B, T), dtype=torch.int32, device=dev),
-              "input_ids": torch.empty((B, T), dtype=torch.int32, device=dev)}
+
+        def mk():
+            return {"pixel_values": torch.empty(key[0], dtype=F32, device=dev),
+                    "decoder_input_ids": torch.empty((B, T), dtype=torch.int32, device=dev),
+                    "attention_mask": torch.empty((B, T), dtype=torch.int32, device=dev),
+                    "input_ids": torch.empty((B, T), dtype=torch.int32, device=dev)}
+        sb = {"key": key, "graph": None, "land": [mk(), mk()], "slot": 0, "copy_stream": torch.cuda.Stream(device=dev),
+              "consumed": [torch.cuda.Event(), torch.cuda.Event()]}
+        sb.update(mk())
         state._static = sb
-    for k in ("pixel_values", "decoder_input_ids", "attention_mask", "input_ids"):
-        sb[k].copy_(torch.as_tensor(batch[k]), non_blocking=True)
+    cur = torch.cuda.current_stream()
+    on_host = not torch.as_tensor(batch["pixel_values"]).is_cuda
+    if on_host:
+        slot = sb["slot"] = sb["slot"] ^ 1
+        land, cs = sb["land"][slot], sb["copy_stream"]
+        cs.wait_event(sb["consumed"][slot])              # the previous reader of this landing slot is done
+        with torch.cuda.stream(cs):
+            for k in _KEYS:
+                src = torch.as_tensor(batch[k])
+                if land[k].dtype != src.dtype:          # land in the SOURCE dtype: pure async memcpy, no host-side cast
+                    land[k] = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                land[k].copy_(src, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        cur.wait_event(ready)
+        for k in _KEYS:
+            sb[k].copy_(land[k], non_blocking=True)
+        sb["consumed"][slot].record(cur)
+    else:
+        for k in _KEYS:
+            sb[k].copy_(torch.as_tensor(batch[k]), non_blocking=True)
     return sb
 
 

@@ -33,7 +33,7 @@ def close(got, want, atol, rtol, what=""):
 @pytest.mark.parametrize("layout", ["kn", "kk", "mm"])
 @pytest.mark.parametrize("shape", [(304, 520, 200), (1024, 768, 768), (128, 256, 64), (72, 1000, 136),
                                    (2048, 1024, 4096)])
-@pytest.mark.parametrize("bn", [0, 128, 192, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
 def test_gemm_layouts(layout, shape, bn):
     M, N, K = shape
     a = rnd(M, K, seed=1)
