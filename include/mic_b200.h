@@ -58,7 +58,10 @@ int mic_ce_finalize(void* stream, const float* pmax, const float* psum, const fl
 int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, const void* E, long long lde,
                         const float* bias, const int* labels, const float* lse, const float* row_w, float conf,
                         float low, int M, int V, int K, void* dlogits, long long ldd);
-/* decode-time lm_head for greedy / beam search [G4,G5]: per slab log-softmax partials + top-8 candidates */
+/* decode-time lm_head for greedy / beam search [G4,G5]: each CTA keeps a running log-softmax partial and a
+ * running top-8 for its rows across all of its vocabulary tiles; partial arrays are
+ * [mic_lm_head_search_num_partials(M), M(, 8)] */
+int mic_lm_head_search_num_partials(int M);
 int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
                        const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
                        float* cand_val, int* cand_idx);
@@ -68,6 +71,10 @@ int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E
  * pre_layrnorm, FlaxMBartDecoderLayer, layernorm_embedding, layer_norm [E2,E5,D5,D6]. x,y bf16 [M,d]. */
 int mic_layernorm_fwd(void* stream, const void* x, const float* gamma, const float* beta, float eps, void* y,
                       float* mean, float* rstd, int M, int d);
+/* decode-time fusion [G4]: x += acc + bias; y = LayerNorm(x); acc = 0.  `acc` (fp32 [M,d]) is the split-K
+ * accumulator the preceding out_proj / fc2 GEMM reduce-added into (mic_gemm_bf16 with accumulate=1). */
+int mic_residual_ln_fwd(void* stream, float* acc, const float* bias, void* x, const float* gamma, const float* beta,
+                        float eps, void* y, int M, int d);
 /* workspaces (floats) for the two reductions below; `counters`: >= 1024 uint32 that the caller zero-initialises
  * ONCE - every kernel hands them back zeroed (ticket counters of the "last CTA reduces" scheme). */
 long long mic_layernorm_bwd_workspace_floats(int M, int d);

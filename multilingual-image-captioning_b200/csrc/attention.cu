@@ -380,11 +380,17 @@ struct DecAttnArgs {
 };
 
 __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  __shared__ float s_p[4][128];
+  __shared__ int s_row[4][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int wid = blockIdx.x * 4 + w;
   if (wid >= a.R * a.H) return;
   const int r = wid / a.H, h = wid % a.H;
-  // q in registers: every lane holds the full 64-d query (as fp32 pairs)
+  const int nk = a.n_keys;
+  // cache rows of the visible history (ancestor table) or the shared visual K/V row
+  const int kvrow_default = r / a.rows_per_kv;
+  for (int j = lane; j < nk; j += 32) s_row[w][j] = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
+  // q in registers: every lane holds the full 64-d query, pre-scaled
   float qv[HD];
   {
     const bf16* qp = a.q + (long long)r * a.ldq + h * HD;
@@ -400,58 +406,74 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs
       }
     }
   }
-  const int kvrow_default = r / a.rows_per_kv;
+  __syncwarp();
+  // scores: lane handles keys lane, lane+32, ... (8 independent 16-byte loads per key)
   float mx = -INFINITY;
-  float sc[4];   // up to 128 keys
-  const int nk = a.n_keys;
+  float sc[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int j = lane + i * 32;
-    float s = -INFINITY;
+    float sdot = -INFINITY;
     if (j < nk) {
-      const int row = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
-      const bf16* kp = a.kc + ((long long)row * a.T + j) * a.ldkv + h * HD;
+      const bf16* kp = a.kc + ((long long)s_row[w][j] * a.T + j) * a.ldkv + h * HD;
+      uint4 kk[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kk[c] = *reinterpret_cast<const uint4*>(kp + c * 8);
       float acc = 0.f;
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(kp + c);
-        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&kk[c]);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const float2 f = unpack_bf16(uu[jj]);
-          acc += qv[c + 2 * jj] * f.x + qv[c + 2 * jj + 1] * f.y;
+          acc = fmaf(qv[c * 8 + 2 * jj], f.x, acc);
+          acc = fmaf(qv[c * 8 + 2 * jj + 1], f.y, acc);
         }
       }
-      s = acc;
+      sdot = acc;
     }
-    sc[i] = s;
-    mx = fmaxf(mx, s);
+    sc[i] = sdot;
+    mx = fmaxf(mx, sdot);
   }
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    sc[i] = (lane + i * 32 < nk) ? __expf(sc[i] - mx) : 0.f;
-    sum += sc[i];
+    const int j = lane + i * 32;
+    const float p = (j < nk) ? __expf(sc[i] - mx) : 0.f;
+    if (j < nk) s_p[w][j] = p;
+    sum += p;
   }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-  // output: lane owns dims 2*lane, 2*lane+1 ; loop keys, broadcast p via shuffle
-  float o0 = 0.f, o1 = 0.f;
+  __syncwarp();
+  // P.V: 4 key groups x 8 dim groups; lane (kg, dl) accumulates dims dl*8..dl*8+7 over keys kg, kg+4, ...
+  const int kg = lane >> 3, dl = lane & 7;
+  float o[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = i * 32 + jj;
-      if (j >= nk) break;   // warp-uniform
-      const float p = __shfl_sync(0xffffffffu, sc[i], jj);
-      const int row = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
-      const bf16* vp = a.vc + ((long long)row * a.T + j) * a.ldkv + h * HD;
-      const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(vp + 2 * lane));
-      o0 += p * f.x;
-      o1 += p * f.y;
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int j = kg; j < nk; j += 4) {
+    const bf16* vp = a.vc + ((long long)s_row[w][j] * a.T + j) * a.ldkv + h * HD + dl * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(vp);
+    const float p = s_p[w][j];
+    const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float2 f = unpack_bf16(uu[jj]);
+      o[2 * jj] = fmaf(p, f.x, o[2 * jj]);
+      o[2 * jj + 1] = fmaf(p, f.y, o[2 * jj + 1]);
     }
   }
-  *reinterpret_cast<uint32_t*>(a.o + (long long)r * a.ldo + h * HD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (kg == 0) {
+    *reinterpret_cast<uint4*>(a.o + (long long)r * a.ldo + h * HD + dl * 8) =
+        make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                   pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
+  }
 }
 
 }  // namespace

@@ -85,6 +85,51 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Decode-time fusion: x += acc + bias ; y = LayerNorm(x) ; acc = 0.
+// `acc` is the fp32 split-K accumulator a residual GEMM reduce-added into (TMA reduce-add); zeroing it
+// here keeps it ready for the next GEMM without a memset launch.  One warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+residual_ln_fwd_kernel(float* __restrict__ acc, const float* __restrict__ bias, bf16* __restrict__ x,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       bf16* __restrict__ y, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float v[LN_MAX_ITERS][8];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float a[8], b[8];
+      load8(x + (long long)row * d + c, v[it]);
+      load8f(acc + (long long)row * d + c, a);
+      load8f(bias + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[it][j] = bf16_round(v[it][j] + a[j] + b[j]);
+      store8(x + (long long)row * d + c, v[it]);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(acc + (long long)row * d + c) = z;
+      *reinterpret_cast<float4*>(acc + (long long)row * d + c + 4) = z;
+    }
+  }
+  float mean, rstd;
+  ln_stats(v, d, lane, &mean, &rstd, eps);
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + b[j];
+      store8(y + (long long)row * d + c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm backward, two kernels:
 //  (1) dx = dres + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))   one warp per row, lean registers
 //  (2) dgamma = sum_rows dy*xhat, dbeta = sum_rows dy : column-parallel over row chunks; the last CTA of a
@@ -590,6 +635,14 @@ extern "C" int mic_layernorm_fwd(void* stream, const void* x, const float* gamma
                                  void* y, float* mean, float* rstd, int M, int d) {
   MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm: d=%d must be a multiple of 8 and <= 1024", d);
   layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, M, d);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_residual_ln_fwd(void* stream, float* acc, const float* bias, void* x, const float* gamma,
+                                   const float* beta, float eps, void* y, int M, int d) {
+  MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "residual_ln: d=%d must be a multiple of 8 and <= 1024", d);
+  residual_ln_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(acc, bias, (bf16*)x, gamma, beta, eps, (bf16*)y, M, d);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

@@ -265,12 +265,32 @@ extern "C" int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, c
   return launch_one<0, 0, 256, EpiCEGrad>(reinterpret_cast<cudaStream_t>(stream), o, ep);
 }
 
+// partial lists per row produced by mic_lm_head_search (one per epilogue half of each CTA serving the row's m-block)
+static int search_grid(int M) {
+  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  int g = (mic_num_sms() / mb) * mb;
+  return g < mb ? mb : g;
+}
+extern "C" int mic_lm_head_search_num_partials(int M) { return 2 * (search_grid(M) / ((M + BLOCK_M - 1) / BLOCK_M)); }
+
 extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
                                   const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
                                   float* cand_val, int* cand_idx) {
+  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  MIC_CHECK_ARG(mb <= mic_num_sms(), "lm_head_search: M=%d rows exceed one m-block per SM", M);
   Operands o;
-  int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, (M + BLOCK_M - 1) / BLOCK_M);
+  int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, mb);
   if (rc) return rc;
   EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx};
-  return launch_one<0, 0, 256, EpiSearch>(reinterpret_cast<cudaStream_t>(stream), o, ep);
+  // fixed m-block per CTA: grid is a multiple of num_m_blocks and tiles are rasterised m-fastest
+  auto kern = gemm_kernel<0, 0, 256, EpiSearch>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
+      o.ta, o.tb, o.td, o.td2, o.shape, ep);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
 }

@@ -116,6 +116,8 @@ struct EpiStoreParams {
 struct EpiStore {
   typedef EpiStoreParams Params;
   struct State {};
+  __device__ static void kernel_begin(const Params&, State&) {}
+  __device__ static void kernel_end(const Params&, State&, const Shape&, int, int) {}
   __device__ static void tile_begin(const Params&, State&, const Shape&, int, int, int) {}
   __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
 
@@ -259,6 +261,8 @@ struct EpiCEStats {
     float mx, sm, sz;
     int label;
   };
+  __device__ static void kernel_begin(const Params&, State&) {}
+  __device__ static void kernel_end(const Params&, State&, const Shape&, int, int) {}
   __device__ static void tile_begin(const Params& p, State& st, const Shape& s, int row, int, int) {
     st.mx = -INFINITY;
     st.sm = 0.f;
@@ -335,6 +339,8 @@ struct EpiCEGrad {
     float lse2, w;
     int label;
   };
+  __device__ static void kernel_begin(const Params&, State&) {}
+  __device__ static void kernel_end(const Params&, State&, const Shape&, int, int) {}
   __device__ static void tile_begin(const Params& p, State& st, const Shape& s, int row, int, int) {
     const bool ok = row < s.M;
     st.lse2 = ok ? p.lse[row] * MIC_LOG2E : 0.f;
@@ -394,12 +400,15 @@ constexpr int SEARCH_TOPK = 8;
 struct EpiSearchParams {
   const float* bias;   // [N] or null
   int mask_token;      // FlaxMinLengthLogitsProcessor: this token id scores -inf (-1 = none)
-  float* pmax;         // [2*num_n_blocks, M]
-  float* psum;         // [2*num_n_blocks, M]
-  float* cand_val;     // [2*num_n_blocks, M, SEARCH_TOPK] raw logits (descending)
-  int* cand_idx;       // [2*num_n_blocks, M, SEARCH_TOPK] vocab ids
+  float* pmax;         // [num_partials, M]
+  float* psum;         // [num_partials, M]
+  float* cand_val;     // [num_partials, M, SEARCH_TOPK] raw logits (descending)
+  int* cand_idx;       // [num_partials, M, SEARCH_TOPK] vocab ids
 };
 
+// The launcher sizes the grid as a multiple of num_m_blocks with group_m == num_m_blocks, so every CTA
+// keeps the SAME m-block for all of its tiles: the running (max, sum) and the running top-8 of a row live
+// in registers across the whole kernel and are written once (partial slot = CTA rank within the m-block).
 struct EpiSearch {
   typedef EpiSearchParams Params;
   struct State {
@@ -407,7 +416,7 @@ struct EpiSearch {
     float tv[SEARCH_TOPK];
     int ti[SEARCH_TOPK];
   };
-  __device__ static void tile_begin(const Params&, State& st, const Shape&, int, int, int) {
+  __device__ static void kernel_begin(const Params&, State& st) {
     st.mx = -INFINITY;
     st.sm = 0.f;
 #pragma unroll
@@ -416,48 +425,69 @@ struct EpiSearch {
       st.ti[i] = 0x7fffffff;
     }
   }
+  __device__ static void tile_begin(const Params&, State&, const Shape&, int, int, int) {}
+  __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
   __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
     if (col0 >= s.N) return;
-    float cmax = -INFINITY;
+    const bool full = col0 + 64 <= s.N;
+    const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    if (full && (bias_vec || !p.bias)) {
+      if (p.bias) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      const int c = col0 + j;
-      float z = v[j];
-      if (c < s.N && c != p.mask_token) {
-        if (p.bias) z += p.bias[c];
-      } else {
-        z = -INFINITY;
+        for (int u = 0; u < 16; ++u) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + u * 4);
+          v[u * 4 + 0] += b.x; v[u * 4 + 1] += b.y; v[u * 4 + 2] += b.z; v[u * 4 + 3] += b.w;
+        }
       }
-      v[j] = z;
-      cmax = fmaxf(cmax, z);
-      // sorted insert (descending; on ties the earlier = lower index stays ahead: strict >)
-      if (z > st.tv[SEARCH_TOPK - 1]) {
-        float cv = z;
-        int ci = c;
+    } else {
 #pragma unroll
-        for (int i = 0; i < SEARCH_TOPK; ++i) {
-          if (cv > st.tv[i]) {
-            const float tvv = st.tv[i];
-            const int tii = st.ti[i];
-            st.tv[i] = cv;
-            st.ti[i] = ci;
-            cv = tvv;
-            ci = tii;
+      for (int j = 0; j < 64; ++j) {
+        const int c = col0 + j;
+        v[j] = (c < s.N) ? (p.bias ? v[j] + p.bias[c] : v[j]) : -INFINITY;
+      }
+    }
+    const unsigned mrel = static_cast<unsigned>(p.mask_token - col0);
+    if (mrel < 64u) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = (mrel == static_cast<unsigned>(j)) ? -INFINITY : v[j];
+    }
+    float cmax = v[0];
+#pragma unroll
+    for (int j = 1; j < 64; ++j) cmax = fmaxf(cmax, v[j]);
+    if (cmax > st.tv[SEARCH_TOPK - 1]) {
+      // rare once the running threshold has risen: sorted insert (descending; strict > keeps the lower
+      // index ahead on ties because columns are visited in ascending order)
+#pragma unroll 8
+      for (int j = 0; j < 64; ++j) {
+        if (v[j] > st.tv[SEARCH_TOPK - 1]) {
+          float cv = v[j];
+          int ci = col0 + j;
+#pragma unroll
+          for (int i = 0; i < SEARCH_TOPK; ++i) {
+            if (cv > st.tv[i]) {
+              const float tvv = st.tv[i];
+              const int tii = st.ti[i];
+              st.tv[i] = cv;
+              st.ti[i] = ci;
+              cv = tvv;
+              ci = tii;
+            }
           }
         }
       }
     }
     const float nm = fmaxf(st.mx, cmax);
     if (nm == -INFINITY) return;                   // every column masked so far
+    const float nm2 = nm * MIC_LOG2E;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc += __expf(v[j] - nm);
-    st.sm = st.sm * __expf(st.mx - nm) + acc;
+    for (int j = 0; j < 64; ++j) acc += exp2f(fmaf(v[j], MIC_LOG2E, -nm2));
+    st.sm = st.sm * exp2f((st.mx - nm) * MIC_LOG2E) + acc;
     st.mx = nm;
   }
-  __device__ static void tile_end(const Params& p, State& st, const Shape& s, int row, int, int n_blk, int half) {
+  __device__ static void kernel_end(const Params& p, State& st, const Shape& s, int row, int slot) {
     if (row >= s.M) return;
-    const long long o = (long long)(n_blk * 2 + half) * s.M + row;
+    const long long o = (long long)slot * s.M + row;
     p.pmax[o] = st.mx;
     p.psum[o] = st.sm;
 #pragma unroll
@@ -608,6 +638,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     ctx.tmap_d2 = &tmap_d2;
     uint32_t it = 0;
     typename Epi::State st;
+    Epi::kernel_begin(ep, st);
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
       const TileCoord tc = tile_coord(shape, u % num_tiles);
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -637,6 +668,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       Epi::tile_end(ep, st, shape, ctx.row, tc.m_blk, tc.n_blk, half);
     }
+    // persistent-state policies flush once: this CTA's fixed m-block is blockIdx.x % num_m_blocks
+    Epi::kernel_end(ep, st, shape, (int)(blockIdx.x % shape.num_m_blocks) * BLOCK_M + quarter * 32 + lane,
+                    (int)(blockIdx.x / shape.num_m_blocks) * 2 + half);
     if (lane == 0) tma_store_wait_all();            // staged tiles fully written before the CTA retires
   }
   tcgen05_fence_before();

@@ -218,12 +218,18 @@ class CaptionEngine:
     # training forward + backward: fills ps.grad, returns the CE workspace (ws["out"][0] = loss)
     # ------------------------------------------------------------------------------------------
     def forward_backward(self, pixel_values, decoder_input_ids, attention_mask, labels, label_smoothing=0.0,
-                         position_ids=None):
+                         position_ids=None, stage=0):
+        """stage 0: the whole step.  stage 1: forward + backward down to the cross-K/V projection (every
+        gradient stored before `grad_split_offset()` is final afterwards: lm_head bias, tied embedding, decoder,
+        cross K/V) — stage 2: visual projection + vision encoder backward.  The two-stage form lets the
+        data-parallel all-reduce of the first 84 % of the gradient overlap the vision backward."""
         c, t, ps, b = self.c, self.t, self.ps, self.bufs
         ps.ensure_grad()
         B, T = decoder_input_ids.shape
         S, dv, d = c.num_tokens, c.hidden_size, t.d_model
         M, Mv = B * T, B * S
+        if stage == 2:
+            return self._backward_vision(B, S, Mv, dv, d)
         ids = decoder_input_ids.to(self.dev, I32).contiguous().view(-1)
         km = attention_mask.to(self.dev, I32).contiguous()
         lab = labels.to(self.dev, I32).contiguous().view(-1)
@@ -295,9 +301,23 @@ class CaptionEngine:
         else:
             ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), None, B, T)
             gpos.index_add_(0, (pos + t.position_offset).long(), demb.float())   # rare path (explicit position ids)
-        # ---------------- backward: cross K/V projection, visual projection ----------------
+        # ---------------- backward: cross K/V projection ----------------
         d_enc = b.get("tr.d_enc", (Mv, d))
         self._dense_bwd(enc, d_enc_kv, "d.ca_kv", d_enc)
+        if stage == 1:
+            return ws
+        self._backward_vision(B, S, Mv, dv, d)
+        return ws
+
+    def grad_split_offset(self):
+        """Flat-buffer offset separating the gradients finished by stage 1 from those of stage 2."""
+        return self.ps.layout.storages["proj.w"][0]
+
+    def _backward_vision(self, B, S, Mv, dv, d):
+        c, t, ps, b = self.c, self.t, self.ps, self.bufs
+        enc = b.t["tr.enc.out"]
+        d_enc = b.t["tr.d_enc"]
+        # ---------------- backward: visual projection ----------------
         te = "tr.enc"
         L = c.num_hidden_layers
         x_last = b.t[te + ".post"] if c.final_layernorm else b.t[te + f".x{L}"]
@@ -345,4 +365,3 @@ class CaptionEngine:
             ops.act_bwd_colsum(dpo, None, "none", None, ps.g("v.patch.b"), self._workspace(
                 ops.colsum_workspace_floats(dpo.shape[0], dv)))
         ops.gemm(b.t[te + ".patches"], dpo, a_mn=True, b_mn=True, out=ps.g("v.patch.w"))
-        return ws

@@ -82,6 +82,10 @@ def lm_head_num_partials(V):
     return lib().mic_lm_head_num_partials(V)
 
 
+def lm_head_search_num_partials(M):
+    return lib().mic_lm_head_search_num_partials(M)
+
+
 def lm_head_ce_stats(h, emb, bias, labels, ws):
     M, K = h.shape
     V = emb.shape[0]
@@ -122,6 +126,12 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, mean=None, rstd=None):
     if out is None:
         out = torch.empty_like(x)
     _call("mic_layernorm_fwd", _p(x), _p(gamma), _p(beta), float(eps), _p(out), _p(mean), _p(rstd), M, d)
+    return out
+
+
+def residual_ln_fwd(acc, bias, x, gamma, beta, eps, out):
+    M, d = x.shape
+    _call("mic_residual_ln_fwd", _p(acc), _p(bias), _p(x), _p(gamma), _p(beta), float(eps), _p(out), M, d)
     return out
 
 

@@ -59,6 +59,7 @@ class TrainState:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_elems = max(int(bucket_bytes) // 4, 1)
         self.metrics_buf = torch.zeros(2, dtype=F32, device=self.store.device)
+        self.comm_stream = None
 
     @classmethod
     def create(cls, apply_fn=None, params=None, tx=None, model=None, **kw):
@@ -72,11 +73,28 @@ class TrainState:
     def opt_state(self):
         return {"count": self.step, "mu": self.store.tree(self.store.adam_m), "nu": self.store.tree(self.store.adam_v)}
 
-    def allreduce_grads(self):
-        """lax.pmean(grad, 'batch'): SUM over ranks here, the 1/N is folded into the AdamW kernel."""
+    def allreduce_grads(self, lo=0, hi=None, async_stream=False):
+        """lax.pmean(grad, 'batch') over grad[lo:hi]: SUM over ranks here, the 1/N is folded into the AdamW kernel.
+        async_stream=True issues the collective on a dedicated communication stream that first waits for the
+        work already enqueued on the compute stream (so it overlaps whatever is enqueued afterwards)."""
         if self.world == 1:
             return
-        bucketed_allreduce_sum(self.store.grad, self.bucket_elems)
+        g = self.store.grad
+        hi = g.numel() if hi is None else hi
+        if not async_stream:
+            bucketed_allreduce_sum(g[lo:hi], self.bucket_elems)
+            return
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.store.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            bucketed_allreduce_sum(g[lo:hi], self.bucket_elems)
+
+    def wait_comm(self):
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def apply_gradients(self):
         """optax.adamw with the schedule evaluated at the pre-increment count."""
@@ -158,22 +176,60 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
     eng = state.model.engine
     sb = _static_batch(state, batch)
     args = (sb["pixel_values"], sb["decoder_input_ids"], sb["attention_mask"], sb["input_ids"])
+    ls = label_smoothing_factor
+    dp = state.world > 1
+    stages = (1, 2) if dp else (0,)      # data parallel: two graph segments so the all-reduce can overlap
+
+    def run_stage(stage):
+        return eng.forward_backward(*args, label_smoothing=ls, stage=stage)
+
+    def between():
+        # lax.pmean of everything produced so far (lm_head bias, tied embedding, decoder, cross K/V = 84 % of
+        # the bytes) on the communication stream while the vision backward keeps the SMs busy
+        if dp:
+            state.allreduce_grads(0, eng.grad_split_offset(), async_stream=True)
+
     if not use_cuda_graph:
-        ws = eng.forward_backward(*args, label_smoothing=label_smoothing_factor)
-    elif sb["graph"] is None or sb.get("ls") != label_smoothing_factor:
-        ws = eng.forward_backward(*args, label_smoothing=label_smoothing_factor)      # eager: allocates all buffers
+        ws = None
+        for st in stages:
+            r = run_stage(st)
+            ws = r if r is not None else ws
+            if st == 1:
+                between()
+    elif sb["graph"] is None or sb.get("ls") != ls:
+        ws = None
+        for st in stages:                                           # eager: allocates all buffers
+            r = run_stage(st)
+            ws = r if r is not None else ws
+            if st == 1:
+                between()
         if sb.get("warm"):
+            state.wait_comm()
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                ws = eng.forward_backward(*args, label_smoothing=label_smoothing_factor)
-            sb["graph"], sb["ws"], sb["ls"] = g, ws, label_smoothing_factor
-            g.replay()
+            graphs = []
+            for st in stages:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    r = run_stage(st)
+                if r is not None:
+                    sb["ws"] = r
+                graphs.append(g)
+            sb["graph"], sb["ls"] = graphs, ls
+            ws = sb["ws"]
+            for i, g in enumerate(graphs):
+                g.replay()
+                if stages[i] == 1:
+                    between()
         sb["warm"] = True
     else:
-        sb["graph"].replay()
+        for i, g in enumerate(sb["graph"]):
+            g.replay()
+            if stages[i] == 1:
+                between()
         ws = sb["ws"]
-    state.allreduce_grads()
+    if dp:
+        state.allreduce_grads(eng.grad_split_offset(), None, async_stream=True)
+        state.wait_comm()
     lr = state.apply_gradients()
     loss = ws["out"][0:1].clone()
     if state.world > 1:

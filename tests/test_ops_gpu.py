@@ -337,7 +337,7 @@ def test_lm_head_search_and_merge():
     V, K, R = 5003, 128, 24
     h, E = rnd(R, K, seed=80), rnd(V, K, seed=81, scale=0.3)
     bias = rnd(V, seed=82, dtype=torch.float32, scale=0.1)
-    n = ops.lm_head_num_partials(V)
+    n = ops.lm_head_search_num_partials(R)
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=DEV)
     ws = {"nparts": n, "pmax": f(n, R), "psum": f(n, R), "cand_val": f(n, R, 8),
           "cand_idx": torch.empty(n, R, 8, dtype=torch.int32, device=DEV), "row_lp": f(R, 8),
