@@ -227,7 +227,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "CLIP-ViT-B/32 + mBART-50 training step (fwd+bwd+AdamW), 224x224 images, "
                                "64-token captions", "per_gpu_batch": B, "global_batch": B * world, "seq_len": T,
-                   "parallelism": f"dp{world}", "dropout": 0.0, "cuda_graph": True, "ms_per_step_eager": ms_eager, "l2": "working set (>20 GB/step) exceeds the 126 MB L2",
+                   "parallelism": f"dp{world}", "dropout": state.dropout, "cuda_graph": True, "ms_per_step_eager": ms_eager, "l2": "working set (>20 GB/step) exceeds the 126 MB L2",
                    "loss_last": lossv},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},

@@ -36,11 +36,14 @@ int mic_abi_version(void);
  * patch conv as GEMM [E1], and all their dgrad / wgrad contractions under jax.value_and_grad
  * main.py:696 [L2].  D is bf16 (d_is_f32=0) or fp32; accumulate=1 adds into an fp32 D.
  * D2 (optional, bf16, ld = ldd) receives the pre-activation.  block_n/group_m/split_k = 0 -> auto
- * (split_k > 1 cuts K into slices combined by TMA reduce-add; fp32 outputs only). */
+ * (split_k > 1 cuts K into slices combined by TMA reduce-add; fp32 outputs only).
+ * drop_seed (device u32, null = off): flax.linen.Dropout(rate=drop_p) on the activation output BEFORE the
+ * residual add — FlaxMBartDecoderLayer `hidden_states = residual + dropout(...)`; the mask is a counter
+ * hash of (*drop_seed + drop_site, element index), regenerated identically by mic_act_bwd_colsum. */
 int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, long long lda, const void* B,
                   long long ldb, int M, int N, int K, void* D, long long ldd, int d_is_f32, int accumulate,
                   const float* bias, int act, void* D2, const void* residual, long long ldr, int block_n,
-                  int group_m, int split_k);
+                  int group_m, int split_k, const unsigned int* drop_seed, unsigned int drop_site, float drop_p);
 
 /* ---- tied lm_head fused with log-softmax / label-smoothed CE ------------------------------------
  * modeling_clip_vision_mbart.py:170-178 [H1] + loss_fn main.py:658-680 [L1]; fp32 logits never reach HBM.
@@ -87,12 +90,13 @@ int mic_layernorm_bwd(void* stream, const void* dy, const void* x, const float* 
  * dbias is null).  Backward of Dense bias + ACT2FN [L2]. */
 int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act, void* dU,
                        long long lddu, float* dbias, int accumulate, float* workspace, unsigned int* counters, int M,
-                       int N);
+                       int N, const unsigned int* drop_seed, unsigned int drop_site, float drop_p);
 /* FlaxMBartDecoder embedding [D1]: shared[id]*scale + embed_positions[pos+offset] -> emb -> layernorm_embedding.
  * pos_ids null -> position = row % pos_mod (arange(T), modeling_clip_vision_mbart.py:490-494). */
 int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids, int pos_mod, int pos_offset,
                      const void* table, const void* pos_table, float scale, const float* gamma, const float* beta,
-                     float eps, void* emb, void* y, float* mean, float* rstd, int M, int d);
+                     float eps, void* emb, void* y, float* mean, float* rstd, int M, int d,
+                     const unsigned int* drop_seed, unsigned int drop_site, float drop_p);
 /* backward of the lookup: d_table[id] += d_emb*scale (fp32 atomics onto the tied embedding gradient);
  * d_pos_rows[t] (=) sum_b d_emb[b,t] */
 int mic_embed_bwd(void* stream, const int* ids, const void* d_emb, float scale, float* d_table, float* d_pos_rows,

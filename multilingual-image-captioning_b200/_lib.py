@@ -18,7 +18,7 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argument ctypes (return type is always int unless listed in _RET)
 SIGNATURES = {
     "mic_abi_version": [],
-    "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I],
+    "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I, P, I, F],
     "mic_lm_head_num_partials": [I],
     "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P],
     "mic_ce_finalize": [P, P, P, P, P, P, I, I, I, F, P, P, P, P],
@@ -30,8 +30,8 @@ SIGNATURES = {
     "mic_layernorm_bwd_workspace_floats": [I, I],
     "mic_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I],
     "mic_colsum_workspace_floats": [I, I],
-    "mic_act_bwd_colsum": [P, P, L, P, L, I, P, L, P, I, P, P, I, I],
-    "mic_embed_ln_fwd": [P, P, P, I, I, P, P, F, P, P, F, P, P, P, P, I, I],
+    "mic_act_bwd_colsum": [P, P, L, P, L, I, P, L, P, I, P, P, I, I, P, I, F],
+    "mic_embed_ln_fwd": [P, P, P, I, I, P, P, F, P, P, F, P, P, P, P, I, I, P, I, F],
     "mic_embed_bwd": [P, P, P, F, P, P, I, I, I],
     "mic_batch_sum": [P, P, I, I, I, P, L],
     "mic_patchify": [P, P, P, I, I, I, I, I],

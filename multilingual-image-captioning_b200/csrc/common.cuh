@@ -119,6 +119,33 @@ __device__ __forceinline__ float act_bwd(float x, int act) {  // d act / dx
 }
 
 // ------------------------------------------------------------------------------------------------
+// dropout: counter-based mask, reproducible between forward and backward.  One 32-bit hash (lowbias32) of
+// (element-pair index, seed) yields two 16-bit uniforms; an element is DROPPED when its uniform < thr16.
+// flax.linen.Dropout semantics: kept values are scaled by 1/(1-p).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t drop_hash(uint32_t pair_idx, uint32_t seed) {
+  uint32_t h = pair_idx * 0x9E3779B1u ^ seed;
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
+// keep flags for elements (2*pair_idx, 2*pair_idx+1)
+__device__ __forceinline__ void drop_keep2(uint32_t pair_idx, uint32_t seed, uint32_t thr16, bool* k0, bool* k1) {
+  const uint32_t h = drop_hash(pair_idx, seed);
+  *k0 = (h & 0xFFFFu) >= thr16;
+  *k1 = (h >> 16) >= thr16;
+}
+struct DropoutParams {
+  const uint32_t* seed_ptr;   // device scalar (so a captured graph sees a new seed every replay); null = off
+  uint32_t site;              // distinguishes the dropout sites of one step
+  uint32_t thr16;             // round(p * 65536)
+  float scale;                // 65536 / (65536 - thr16)
+};
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256)
 act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __restrict__ U, long long ldu, int act,
                       bf16* __restrict__ dU, long long lddu, float* __restrict__ part,
                       unsigned int* __restrict__ counters, float* __restrict__ dbias, int accumulate, int M, int N,
-                      int rows_per_chunk) {
+                      int rows_per_chunk, DropoutParams drop) {
   __shared__ float red[8][256 + 8];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + cg * 8;
@@ -283,13 +283,24 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __
     for (int r = r0 + rl; r < r1; r += 8) {
       float g[8];
       load8(dY + (long long)r * ldy + c, g);
+      if (drop.seed_ptr) {          // backward of x + dropout(z): dz = dy * mask / (1-p), same mask as forward
+        const uint32_t seed = *drop.seed_ptr + drop.site;
+        const uint32_t base = ((uint32_t)r * (uint32_t)N + (uint32_t)c) >> 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool k0, k1;
+          drop_keep2(base + j, seed, drop.thr16, &k0, &k1);
+          g[2 * j] = k0 ? bf16_round(g[2 * j] * drop.scale) : 0.f;
+          g[2 * j + 1] = k1 ? bf16_round(g[2 * j + 1] * drop.scale) : 0.f;
+        }
+      }
       if (act != MIC_ACT_NONE) {
         float u[8];
         load8(U + (long long)r * ldu + c, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = bf16_round(g[j] * act_bwd(u[j], act));
-        store8(dU + (long long)r * lddu + c, g);
       }
+      if (dU) store8(dU + (long long)r * lddu + c, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += g[j];
     }
@@ -326,7 +337,8 @@ __global__ void __launch_bounds__(256)
 embed_ln_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, int pos_mod, int pos_offset,
                     const bf16* __restrict__ table, const bf16* __restrict__ pos_table, float scale,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, bf16* __restrict__ emb,
-                    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int d) {
+                    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int d,
+                    DropoutParams drop) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -357,6 +369,17 @@ embed_ln_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids
       load8f(beta + c, b);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + b[j];
+      if (drop.seed_ptr) {
+        const uint32_t seed = *drop.seed_ptr + drop.site;
+        const uint32_t base = ((uint32_t)row * (uint32_t)d + (uint32_t)c) >> 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool k0, k1;
+          drop_keep2(base + j, seed, drop.thr16, &k0, &k1);
+          o[2 * j] = k0 ? o[2 * j] * drop.scale : 0.f;
+          o[2 * j + 1] = k1 ? o[2 * j + 1] * drop.scale : 0.f;
+        }
+      }
       store8(y + (long long)row * d + c, o);
     }
   }
@@ -684,16 +707,23 @@ extern "C" int mic_layernorm_bwd(void* stream, const void* dy, const void* x, co
 
 extern "C" int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, const void* U, long long ldu, int act,
                                   void* dU, long long lddu, float* dbias, int accumulate, float* workspace,
-                                  unsigned int* counters, int M, int N) {
+                                  unsigned int* counters, int M, int N, const unsigned int* drop_seed,
+                                  unsigned int drop_site, float drop_p) {
   MIC_CHECK_ARG(N % 8 == 0 && ldy % 8 == 0, "act_bwd_colsum: N and ld must be multiples of 8");
   MIC_CHECK_ARG(act == MIC_ACT_NONE || (U && dU), "act_bwd_colsum: activation backward needs U and dU");
   const int cb = (N + 255) / 256;
   MIC_CHECK_ARG(cb <= 1024, "act_bwd_colsum: N=%d too wide for the counter array", N);
   const int chunks = pick_chunks(M, cb);
   dim3 grid(cb, chunks);
+  DropoutParams drop;
+  drop.seed_ptr = (drop_seed && drop_p > 0.f) ? drop_seed : nullptr;
+  drop.site = drop_site;
+  drop.thr16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  drop.scale = 65536.0f / (65536.0f - (float)drop.thr16);
+  MIC_CHECK_ARG(!drop.seed_ptr || dU, "act_bwd_colsum: dropout backward needs a dU output");
   act_bwd_colsum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)dY, ldy, (const bf16*)U, ldu, act, (bf16*)dU, lddu,
                                                   workspace, counters, dbias, accumulate, M, N,
-                                                  (M + chunks - 1) / chunks);
+                                                  (M + chunks - 1) / chunks, drop);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
@@ -701,11 +731,16 @@ extern "C" int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, c
 extern "C" int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids, int pos_mod, int pos_offset,
                                 const void* table, const void* pos_table, float scale, const float* gamma,
                                 const float* beta, float eps, void* emb, void* y, float* mean, float* rstd, int M,
-                                int d) {
+                                int d, const unsigned int* drop_seed, unsigned int drop_site, float drop_p) {
   MIC_CHECK_ARG(d % 8 == 0 && d <= 1024, "embed: d=%d must be a multiple of 8 and <= 1024", d);
+  DropoutParams drop;
+  drop.seed_ptr = (drop_seed && drop_p > 0.f) ? drop_seed : nullptr;
+  drop.site = drop_site;
+  drop.thr16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  drop.scale = 65536.0f / (65536.0f - (float)drop.thr16);
   embed_ln_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(ids, pos_ids, pos_mod, pos_offset, (const bf16*)table,
                                                        (const bf16*)pos_table, scale, gamma, beta, eps, (bf16*)emb,
-                                                       (bf16*)y, mean, rstd, M, d);
+                                                       (bf16*)y, mean, rstd, M, d, drop);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

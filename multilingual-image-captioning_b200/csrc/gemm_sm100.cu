@@ -165,7 +165,8 @@ static int launch_bn(cudaStream_t stream, const Operands& o, const typename Epi:
 extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, long long lda,
                              const void* B, long long ldb, int M, int N, int K, void* D, long long ldd, int d_is_f32,
                              int accumulate, const float* bias, int act, void* D2, const void* residual,
-                             long long ldr, int block_n, int group_m, int split_k) {
+                             long long ldr, int block_n, int group_m, int split_k, const unsigned int* drop_seed,
+                             unsigned int drop_site, float drop_p) {
   Operands o;
   const bool splittable = d_is_f32 && !bias && act == MIC_ACT_NONE && !D2 && !residual && split_k != 1 &&
                           ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((ldd * 4) % 16 == 0) && (N % 8 == 0) &&
@@ -185,6 +186,11 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
   ep.residual = reinterpret_cast<const bf16*>(residual);
   ep.ldr = ldr;
   ep.out_scale = 1.0f;
+  ep.drop.seed_ptr = (drop_seed && drop_p > 0.f) ? drop_seed : nullptr;
+  ep.drop.site = drop_site;
+  ep.drop.thr16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  ep.drop.scale = 65536.0f / (65536.0f - (float)ep.drop.thr16);
+  MIC_CHECK_ARG(!(ep.drop.seed_ptr && d_is_f32), "dropout epilogue is for bf16 outputs");
   const int esz = d_is_f32 ? 4 : 2;
   bool tma = ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((ldd * esz) % 16 == 0) && (N % 8 == 0);
   if (bias) tma = tma && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);

@@ -111,6 +111,7 @@ struct EpiStoreParams {
   const bf16* residual; // optional bf16 [M, ldr] added after activation
   long long ldr;
   float out_scale;      // applied to acc before the bias (1.0 normally)
+  DropoutParams drop;   // dropout on the activation output, before the residual add (flax: x + dropout(f(x)))
 };
 
 struct EpiStore {
@@ -132,6 +133,12 @@ struct EpiStore {
       if (p.bias) x += p.bias[c];
       if (p.D2) p.D2[(long long)row * p.ldd + c] = __float2bfloat16_rn(x);
       x = act_fwd(x, p.act);
+      if (p.drop.seed_ptr) {
+        const uint32_t e = (uint32_t)row * (uint32_t)s.N + (uint32_t)c;
+        bool k0, k1;
+        drop_keep2(e >> 1, *p.drop.seed_ptr + p.drop.site, p.drop.thr16, &k0, &k1);
+        x = ((e & 1) ? k1 : k0) ? x * p.drop.scale : 0.f;
+      }
       if (p.residual) x += __bfloat162float(p.residual[(long long)row * p.ldr + c]);
       if (p.d_f32) {
         float* d = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + c;
@@ -202,6 +209,17 @@ struct EpiStore {
     if (p.act != MIC_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = act_fwd(v[j], p.act);
+    }
+    if (p.drop.seed_ptr) {
+      const uint32_t seed = *p.drop.seed_ptr + p.drop.site;
+      const uint32_t base = ((uint32_t)ctx.row * (uint32_t)s.N + (uint32_t)col0) >> 1;   // N, col0 even on this path
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        bool k0, k1;
+        drop_keep2(base + j, seed, p.drop.thr16, &k0, &k1);
+        v[2 * j] = k0 ? v[2 * j] * p.drop.scale : 0.f;
+        v[2 * j + 1] = k1 ? v[2 * j + 1] * p.drop.scale : 0.f;
+      }
     }
     if (p.residual) {
 #pragma unroll

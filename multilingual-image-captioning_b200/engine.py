@@ -51,6 +51,15 @@ class CaptionEngine:
         self.Vp = (self.t.vocab_size + 255) // 256 * 256
         self.emb_scale = math.sqrt(self.t.d_model) if self.t.scale_embedding else 1.0
         self._ws = None
+        # decoder dropout (flax.linen.Dropout, rate = mbart_config.dropout) — active only inside train steps
+        self.dropout_p = 0.0
+        self.drop_seed = torch.zeros(1, dtype=I32, device=self.dev)
+
+    def _drop(self, site):
+        """(seed tensor, site key, p) for dropout site `site` of this step, or None when dropout is off."""
+        if self.dropout_p <= 0.0:
+            return None
+        return (self.drop_seed, (site * 0x9E3779B9) & 0x7FFFFFFF, self.dropout_p)
 
     # ------------------------------------------------------------------------------------------
     def _workspace(self, floats):
@@ -72,7 +81,7 @@ class CaptionEngine:
         return dx
 
     def _dense_bwd(self, x, dy, wname, dx_out, bias=True, w_view=None, gw_view=None, gb_view=None, act=None, u=None,
-                   du=None):
+                   du=None, dropout=None):
         """Backward of y = act(x @ W + b).  x: [M,K] input, dy: [M,N] grad of the output (post-act).
         Returns dx (written into dx_out) — or None if dx_out is None."""
         ps = self.ps
@@ -81,7 +90,12 @@ class CaptionEngine:
         gw = gw_view if gw_view is not None else ps.g(wname + ".w")
         gb = gb_view if gb_view is not None else (ps.g(wname + ".b") if bias else None)
         ws = self._workspace(ops.colsum_workspace_floats(M, N))
-        if act is not None and act != "none":
+        if dropout is not None:
+            # y = residual + dropout(x W + b): the gradient reaching this Dense is dy * mask / (1-p)
+            du = self.bufs.get("tr.dmask", tuple(dy.shape))
+            ops.act_bwd_colsum(dy, None, "none", du, gb, ws, dropout=dropout)
+            dy = du
+        elif act is not None and act != "none":
             ops.act_bwd_colsum(dy, u, act, du, gb, ws)
             dy = du
         elif gb is not None:
@@ -144,7 +158,7 @@ class CaptionEngine:
     # ------------------------------------------------------------------------------------------
     # full-sequence decoder forward (training / eval), returns final hidden states [B*T, d]
     # ------------------------------------------------------------------------------------------
-    def decoder_forward(self, ids, key_mask, pos_ids, enc_kv, B, T, S, save=False, tag="dec"):
+    def decoder_forward(self, ids, key_mask, pos_ids, enc_kv, B, T, S, save=False, tag="dec", train=False):
         t, ps, b = self.t, self.ps, self.bufs
         d, M, H = t.d_model, B * T, t.decoder_attention_heads
         assert t.pre_layernorm, "post-LN (BART) decoder: see engine_postln (config 5)"
@@ -153,8 +167,9 @@ class CaptionEngine:
         emb = b.get(tag + ".emb", (M, d))
         st = (b.get(tag + ".emb.mean", (M,), F32), b.get(tag + ".emb.rstd", (M,), F32))
         x = b.get(tag + ".x0", (M, d))
+        drop = self._drop if train else (lambda site: None)
         ops.embed_ln_fwd(ids, pos_ids, T, t.position_offset, ps.w("shared"), ps.w("d.pos"), self.emb_scale,
-                         ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), eps, emb, x, st[0], st[1])
+                         ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), eps, emb, x, st[0], st[1], dropout=drop(1))
         for l in range(t.decoder_layers):
             n = f"d.{l}"
             sfx = f".{l}" if save else ""
@@ -166,7 +181,7 @@ class CaptionEngine:
             lse1 = b.get(tag + ".lse1" + sfx, (B, H, T), F32)
             ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, lse1, key_mask, True, B, H, T, T, scale)
             x1 = ops.gemm(sa, ps.w(n + ".sa_o.w"), b_mn=True, bias=ps.f(n + ".sa_o.b"), residual=x,
-                          out=b.get(tag + ".x1" + sfx, (M, d)))
+                          out=b.get(tag + ".x1" + sfx, (M, d)), dropout=drop(10 + 4 * l))
             stC = (b.get(tag + ".lnC.mean" + sfx, (M,), F32), b.get(tag + ".lnC.rstd" + sfx, (M,), F32))
             cc = self._ln_fwd(x1, n + ".ln_ca", eps, b.get(tag + ".lnC" + sfx, (M, d)), stC)
             qc = ops.gemm(cc, ps.w(n + ".ca_q.w"), b_mn=True, bias=ps.f(n + ".ca_q.b"), out=b.get(tag + ".qc" + sfx, (M, d)))
@@ -176,14 +191,15 @@ class CaptionEngine:
             vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
             ops.attention_fwd(qc, kl, vl, ca, lse2, None, False, B, H, T, S, scale)
             x2 = ops.gemm(ca, ps.w(n + ".ca_o.w"), b_mn=True, bias=ps.f(n + ".ca_o.b"), residual=x1,
-                          out=b.get(tag + ".x2" + sfx, (M, d)))
+                          out=b.get(tag + ".x2" + sfx, (M, d)), dropout=drop(11 + 4 * l))
             stF = (b.get(tag + ".lnF.mean" + sfx, (M,), F32), b.get(tag + ".lnF.rstd" + sfx, (M,), F32))
             f = self._ln_fwd(x2, n + ".ln_f", eps, b.get(tag + ".lnF" + sfx, (M, d)), stF)
             u = b.get(tag + ".u" + sfx, (M, t.decoder_ffn_dim)) if save else None
             g = ops.gemm(f, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=t.activation_function,
                          pre_act_out=u, out=b.get(tag + ".g" + sfx, (M, t.decoder_ffn_dim)))
             x = ops.gemm(g, ps.w(n + ".fc2.w"), b_mn=True, bias=ps.f(n + ".fc2.b"), residual=x2,
-                         out=b.get(tag + f".x{l + 1}" if save else tag + f".xping{l & 1}", (M, d)))
+                         out=b.get(tag + f".x{l + 1}" if save else tag + f".xping{l & 1}", (M, d)),
+                         dropout=drop(12 + 4 * l))
         if t.final_layer_norm:
             stL = (b.get(tag + ".lnL.mean", (M,), F32), b.get(tag + ".lnL.rstd", (M,), F32))
             x = self._ln_fwd(x, "d.ln_final", eps, b.get(tag + ".hf", (M, d)), stL)
@@ -237,7 +253,7 @@ class CaptionEngine:
         # ---------------- forward ----------------
         enc = self.encode(pixel_values, trunc_int=False, save=True, tag="tr.enc")
         enc_kv = self.cross_kv(enc, tag="tr.enc")
-        hf = self.decoder_forward(ids, km, pos, enc_kv, B, T, S, save=True, tag="tr.dec")
+        hf = self.decoder_forward(ids, km, pos, enc_kv, B, T, S, save=True, tag="tr.dec", train=True)
         ws = self.loss_forward(hf, lab, km.view(-1), label_smoothing)
         # ---------------- backward: lm_head + CE ----------------
         V = t.vocab_size
@@ -272,12 +288,12 @@ class CaptionEngine:
             g_, u_, lnF = b.t[tg + ".g" + sfx], b.t[tg + ".u" + sfx], b.t[tg + ".lnF" + sfx]
             x2, x1, x0 = b.t[tg + ".x2" + sfx], b.t[tg + ".x1" + sfx], b.t[tg + f".x{l}"]
             # FFN
-            self._dense_bwd(g_, dx, n + ".fc2", dg)
+            self._dense_bwd(g_, dx, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
             self._dense_bwd(lnF, dg, n + ".fc1", dtmp, act=t.activation_function, u=u_, du=du)
             self._ln_bwd(dtmp, x2, n + ".ln_f", (b.t[tg + ".lnF.mean" + sfx], b.t[tg + ".lnF.rstd" + sfx]), dx, dx)
             # cross attention
             ca, qc, lnC = b.t[tg + ".ca" + sfx], b.t[tg + ".qc" + sfx], b.t[tg + ".lnC" + sfx]
-            self._dense_bwd(ca, dx, n + ".ca_o", dtmp)
+            self._dense_bwd(ca, dx, n + ".ca_o", dtmp, dropout=self._drop(11 + 4 * l))
             kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
             vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
             ops.attention_bwd(qc, kl, vl, ca, dtmp, b.t[tg + ".lse2" + sfx], None, False, dqc,
@@ -287,12 +303,17 @@ class CaptionEngine:
             self._ln_bwd(dtmp, x1, n + ".ln_ca", (b.t[tg + ".lnC.mean" + sfx], b.t[tg + ".lnC.rstd" + sfx]), dx, dx)
             # self attention
             sa, qkv, lnA = b.t[tg + ".sa" + sfx], b.t[tg + ".qkv" + sfx], b.t[tg + ".lnA" + sfx]
-            self._dense_bwd(sa, dx, n + ".sa_o", dtmp)
+            self._dense_bwd(sa, dx, n + ".sa_o", dtmp, dropout=self._drop(10 + 4 * l))
             ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, dtmp, b.t[tg + ".lse1" + sfx], km, True,
                               dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, T, T, scale)
             self._dense_bwd(lnA, dqkv, n + ".sa_qkv", dtmp)
             self._ln_bwd(dtmp, x0, n + ".ln_sa", (b.t[tg + ".lnA.mean" + sfx], b.t[tg + ".lnA.rstd" + sfx]), dx, dx)
         # embedding
+        if self._drop(1) is not None:       # dropout after layernorm_embedding
+            dmask = b.get("tr.dmask", (M, d))
+            ops.act_bwd_colsum(dx, None, "none", dmask, None, self._workspace(ops.colsum_workspace_floats(M, d)),
+                               dropout=self._drop(1))
+            dx = dmask
         demb = self._ln_bwd(dx, b.t[tg + ".emb"], "d.ln_emb", (b.t[tg + ".emb.mean"], b.t[tg + ".emb.rstd"]), None, dtmp)
         gpos = ps.g("d.pos")
         gpos.zero_()

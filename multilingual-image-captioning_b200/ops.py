@@ -42,6 +42,13 @@ def _call(name, *args):
     check(getattr(lib(), name)(_s(), *args), name)
 
 
+def _drop(dropout):
+    """dropout = (seed_tensor (device int32[1]), site:int, p:float) or None -> C-ABI triple"""
+    if dropout is None or dropout[2] <= 0.0:
+        return None, 0, 0.0
+    return dropout[0].data_ptr(), int(dropout[1]) & 0xFFFFFFFF, float(dropout[2])
+
+
 def _ld(t):
     assert t.dim() == 2 and t.stride(1) == 1, f"need a row-major 2-D view, got {tuple(t.shape)} {t.stride()}"
     return t.stride(0)
@@ -51,7 +58,7 @@ def _ld(t):
 # GEMM family
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, act="none", pre_act_out=None,
-         residual=None, accumulate=False, block_n=0, group_m=0, split_k=0):
+         residual=None, accumulate=False, block_n=0, group_m=0, split_k=0, dropout=None):
     """D[M,N] = act(A[M,K] B[N,K]^T + bias) + residual.
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True, Flax kernel)."""
     assert a.dtype == BF16 and b.dtype == BF16
@@ -74,7 +81,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, a
         assert bias.dtype == F32 and bias.numel() == N
     _call("mic_gemm_bf16", int(a_mn), int(b_mn), _p(a), _ld(a), _p(b), _ld(b), M, N, K, _p(out), _ld(out),
           int(d_f32), int(accumulate), _p(bias), ACT[act], _p(pre_act_out), _p(residual),
-          _ld(residual) if residual is not None else 0, block_n, group_m, split_k)
+          _ld(residual) if residual is not None else 0, block_n, group_m, split_k, *_drop(dropout))
     return out
 
 
@@ -164,18 +171,19 @@ def colsum_workspace_floats(M, N):
     return lib().mic_colsum_workspace_floats(M, N)
 
 
-def act_bwd_colsum(dy, u, act, du, dbias, workspace, accumulate=False):
+def act_bwd_colsum(dy, u, act, du, dbias, workspace, accumulate=False, dropout=None):
     M, N = dy.shape
     _call("mic_act_bwd_colsum", _p(dy), _ld(dy), _p(u), _ld(u) if u is not None else 0, ACT[act], _p(du),
-          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), _p(counters(dy.device)), M, N)
+          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), _p(counters(dy.device)), M, N,
+          *_drop(dropout))
 
 
 def embed_ln_fwd(ids, pos_ids, pos_mod, pos_offset, table, pos_table, scale, gamma, beta, eps, emb, out,
-                 mean=None, rstd=None):
+                 mean=None, rstd=None, dropout=None):
     M = ids.numel()
     d = table.shape[1]
     _call("mic_embed_ln_fwd", _p(ids), _p(pos_ids), int(pos_mod), int(pos_offset), _p(table), _p(pos_table),
-          float(scale), _p(gamma), _p(beta), float(eps), _p(emb), _p(out), _p(mean), _p(rstd), M, d)
+          float(scale), _p(gamma), _p(beta), float(eps), _p(emb), _p(out), _p(mean), _p(rstd), M, d, *_drop(dropout))
     return out
 
 

@@ -47,7 +47,7 @@ class TrainState:
     """flax TrainState analogue (main.py:247-251,638): params + AdamW state + step, living on the GPU."""
 
     def __init__(self, model, learning_rate_fn, b1=0.9, b2=0.999, eps=1e-8, weight_decay=0.0,
-                 bucket_bytes=256 << 20):
+                 bucket_bytes=256 << 20, dropout=None, dropout_seed=0):
         self.model = model
         self.store = model.store
         self.store.ensure_optimizer()
@@ -60,6 +60,12 @@ class TrainState:
         self.bucket_elems = max(int(bucket_bytes) // 4, 1)
         self.metrics_buf = torch.zeros(2, dtype=F32, device=self.store.device)
         self.comm_stream = None
+        # train=True semantics (main.py:692): decoder dropout at mbart_config.dropout unless overridden;
+        # one fresh mask per step and per rank (dropout_rng split / shard_prng_key, main.py:251,686)
+        self.dropout = model.config.mbart_config.dropout if dropout is None else float(dropout)
+        self.dropout_seed = int(dropout_seed)
+        self.seed_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.rank = dist.get_rank() if self.world > 1 else 0
 
     @classmethod
     def create(cls, apply_fn=None, params=None, tx=None, model=None, **kw):
@@ -174,14 +180,19 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
     The forward+backward kernel sequence is shape-static, so after one eager step it is captured into a
     CUDA graph and replayed (no per-kernel host launch cost); the NCCL all-reduce and AdamW stay outside."""
     eng = state.model.engine
+    eng.dropout_p = state.dropout
+    if state.dropout > 0.0:
+        mix = (state.dropout_seed * 1000003 + state.step * 7919 + state.rank * 104729 + 12345) & 0x3FFFFFFF
+        state.seed_host[0] = mix
+        eng.drop_seed.copy_(state.seed_host, non_blocking=True)
     sb = _static_batch(state, batch)
     args = (sb["pixel_values"], sb["decoder_input_ids"], sb["attention_mask"], sb["input_ids"])
-    ls = label_smoothing_factor
+    ls = (label_smoothing_factor, state.dropout)
     dp = state.world > 1
     stages = (1, 2) if dp else (0,)      # data parallel: two graph segments so the all-reduce can overlap
 
     def run_stage(stage):
-        return eng.forward_backward(*args, label_smoothing=ls, stage=stage)
+        return eng.forward_backward(*args, label_smoothing=label_smoothing_factor, stage=stage)
 
     def between():
         # lax.pmean of everything produced so far (lm_head bias, tied embedding, decoder, cross K/V = 84 % of

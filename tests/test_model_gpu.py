@@ -86,7 +86,7 @@ def test_gradients_match_oracle_autograd():
 def test_train_steps_follow_oracle_adamw():
     cfg, params, batch, model = _setup(layers=1)
     sched = mic_b200.create_learning_rate_fn(1000, 10, 1, 2, 1e-2)
-    state = mic_b200.TrainState(model, sched, weight_decay=0.01)
+    state = mic_b200.TrainState(model, sched, weight_decay=0.01, dropout=0.0)   # oracle comparison: deterministic
     losses = []
     p_ref = {k: v.copy() for k, v in _flat(params)}
     m_ref = {k: np.zeros_like(v) for k, v in p_ref.items()}
@@ -199,3 +199,21 @@ def test_generate_cuda_graph_replay_equals_eager():
     g1 = model.generate(batch["pixel_values"], num_beams=1, max_length=12, forced_bos_token_id=1001)
     g2 = model.generate(batch["pixel_values"], num_beams=1, max_length=12, forced_bos_token_id=1001)
     assert torch.equal(g1.sequences, g2.sequences)
+
+
+def test_train_step_with_dropout_runs_and_differs_per_step():
+    """train=True semantics: decoder dropout 0.1 (mbart_config.dropout) with a fresh mask every step."""
+    cfg, params, batch, model = _setup(layers=2)
+    assert cfg.mbart_config.dropout == 0.1
+    state = mic_b200.TrainState(model, lambda step: 0.0)          # lr 0: parameters frozen, only the masks change
+    losses = []
+    for _ in range(4):                                             # eager, warm, capture, replay
+        state, m = mic_b200.train_step(state, batch)
+        losses.append(float(m["loss"]))
+    det = float(model.loss(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"], batch["input_ids"]))
+    assert all(np.isfinite(losses))
+    assert len(set(round(l, 5) for l in losses)) == 4, losses     # new mask each step (also under graph replay)
+    assert all(abs(l - det) < 0.5 for l in losses) and any(abs(l - det) > 1e-4 for l in losses)
+    state0 = mic_b200.TrainState(model, lambda step: 0.0, dropout=0.0)
+    _, m0 = mic_b200.train_step(state0, batch)
+    assert abs(float(m0["loss"]) - det) < 2e-3

@@ -372,3 +372,34 @@ def test_gemm_split_k_reduce_add(split_k):
     ops.gemm(x, dy, a_mn=True, b_mn=True, out=out, split_k=split_k, accumulate=True)
     torch.cuda.synchronize()
     close(out, 2 * want, 1.0, 1e-2, f"split_k={split_k} accumulate")
+
+
+def test_dropout_mask_is_shared_by_forward_and_backward():
+    M, N, K, p = 512, 256, 128, 0.1
+    a, w = rnd(M, K, seed=95, scale=0.5), rnd(K, N, seed=96, scale=0.2)
+    res = rnd(M, N, seed=97)
+    seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    drop = (seed, 77, p)
+    out = ops.gemm(a, w, b_mn=True, residual=res, dropout=drop)
+    plain = ops.gemm(a, w, b_mn=True)
+    torch.cuda.synchronize()
+    z = out.float() - res.float()
+    kept = z.abs() > 1e-3 * plain.float().abs().clamp_min(1e-3)
+    frac = 1.0 - kept.float().mean().item()
+    assert abs(frac - p) < 0.01, frac
+    scale = 65536.0 / (65536.0 - round(p * 65536))
+    close(z[kept], plain.float()[kept] * scale, 3e-2, 2e-2, "kept values scaled by 1/(1-p)")
+    # backward: dz = dy * mask * scale with the SAME mask
+    dy = rnd(M, N, seed=98)
+    du = torch.empty_like(dy)
+    dbias = torch.empty(N, device=DEV)
+    ws = torch.empty(ops.colsum_workspace_floats(M, N), device=DEV)
+    ops.act_bwd_colsum(dy, None, "none", du, dbias, ws, dropout=drop)
+    torch.cuda.synchronize()
+    want = torch.where(kept, dy.float() * scale, torch.zeros_like(dy.float()))
+    strong = plain.float().abs() > 0.05                      # ignore entries whose forward value was ~0 (mask unobservable)
+    close(du.float()[strong], want[strong], 1e-2, 1e-2, "masked dy")
+    # a different site or seed gives a different mask
+    out2 = ops.gemm(a, w, b_mn=True, residual=res, dropout=(seed, 78, p))
+    torch.cuda.synchronize()
+    assert (out2 != out).float().mean().item() > 0.1

@@ -18,7 +18,7 @@ sched = mic_b200.create_learning_rate_fn(1000, 8, 1, 0, 1e-2)
 
 model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg)
 model.params = params
-state = mic_b200.TrainState(model, sched, weight_decay=0.01, bucket_bytes=1 << 16)
+state = mic_b200.TrainState(model, sched, weight_decay=0.01, bucket_bytes=1 << 16, dropout=0.0)
 losses = []
 for step in range(3):      # eager, warm, graph-replay paths
     state, m = mic_b200.train_step(state, shards[rank])
@@ -33,7 +33,7 @@ if rank == 0:
     # single-process reference: mean of shard gradients
     ref = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg)
     ref.params = params
-    rstate = mic_b200.TrainState(ref, sched, weight_decay=0.01)
+    rstate = mic_b200.TrainState(ref, sched, weight_decay=0.01, dropout=0.0)
     rstate.world = 1
     ref_losses = []
     for step in range(3):
