@@ -100,7 +100,7 @@ int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids, int pos_m
 /* backward of the lookup: d_table[id] += d_emb*scale (fp32 atomics onto the tied embedding gradient);
  * d_pos_rows[t] (=) sum_b d_emb[b,t] */
 int mic_embed_bwd(void* stream, const int* ids, const void* d_emb, float scale, float* d_table, float* d_pos_rows,
-                  int B, int T, int d);
+                  int B, int T, int d, int hot_id /* id summed before the atomics (pad token), -1 = none */);
 int mic_batch_sum(void* stream, const void* x, int B, int T, int d, float* out, long long out_ld);
 /* FlaxCLIPVisionEmbeddings / ViT embeddings [E1,V1]: conv(stride=kernel=patch) == GEMM over patches.
  * patchify: fp32 pixels (NHWC, or NCHW per modeling_vit_bart.py:445) -> bf16 [B*g*g, p*p*3] in (kh,kw,c)

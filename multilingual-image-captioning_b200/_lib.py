@@ -32,7 +32,7 @@ SIGNATURES = {
     "mic_colsum_workspace_floats": [I, I],
     "mic_act_bwd_colsum": [P, P, L, P, L, I, P, L, P, I, P, P, I, I, P, I, F],
     "mic_embed_ln_fwd": [P, P, P, I, I, P, P, F, P, P, F, P, P, P, P, I, I, P, I, F],
-    "mic_embed_bwd": [P, P, P, F, P, P, I, I, I],
+    "mic_embed_bwd": [P, P, P, F, P, P, I, I, I, I],
     "mic_batch_sum": [P, P, I, I, I, P, L],
     "mic_patchify": [P, P, P, I, I, I, I, I],
     "mic_vit_embed_ln_fwd": [P, P, P, P, P, P, P, F, I, P, P, P, P, I, I, I],

@@ -389,19 +389,54 @@ embed_ln_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids
   }
 }
 
-// scatter-add of d_emb*scale into the (tied) embedding gradient, fp32 atomics. one warp per row.
+// scatter-add of d_emb*scale into the (tied) embedding gradient, fp32 atomics.  One warp per row, EXCEPT
+// rows whose id is `hot_id` (the pad token: ~40 % of decoder_input_ids, all hitting one table row): those
+// are summed by hot_sum_kernel below and added with a single atomic per column.
 __global__ void __launch_bounds__(256)
 embed_scatter_bwd_kernel(const int* __restrict__ ids, const bf16* __restrict__ d_emb, float scale,
-                         float* __restrict__ d_table, int M, int d) {
+                         float* __restrict__ d_table, int M, int d, int hot_id) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const long long id = ids[row];
+  if (id == hot_id) return;
   for (int c = lane * 8; c < d; c += 256) {
     float g[8];
     load8(d_emb + (long long)row * d + c, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(d_table + id * d + c + j, g[j] * scale);
+  }
+}
+
+// grid = (ceil(d/256), chunks): column sums of the rows with id == hot_id, one atomic per (chunk, column)
+__global__ void __launch_bounds__(256)
+hot_sum_kernel(const int* __restrict__ ids, const bf16* __restrict__ d_emb, float scale, float* __restrict__ d_table,
+               int M, int d, int hot_id, int rows_per_chunk) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < d) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      if (ids[r] != hot_id) continue;
+      float g[8];
+      load8(d_emb + (long long)r * d + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < d) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+    if (sum != 0.f) atomicAdd(d_table + (long long)hot_id * d + col, sum * scale);
   }
 }
 
@@ -746,10 +781,17 @@ extern "C" int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids
 }
 
 extern "C" int mic_embed_bwd(void* stream, const int* ids, const void* d_emb, float scale, float* d_table,
-                             float* d_pos_rows, int B, int T, int d) {
+                             float* d_pos_rows, int B, int T, int d, int hot_id) {
   const int M = B * T;
-  embed_scatter_bwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(ids, (const bf16*)d_emb, scale, d_table, M, d);
+  MIC_CHECK_ARG(d % 8 == 0, "embed_bwd: d must be a multiple of 8");
+  embed_scatter_bwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(ids, (const bf16*)d_emb, scale, d_table, M, d, hot_id);
   MIC_CHECK_LAUNCH();
+  if (hot_id >= 0) {
+    const int chunks = (M + 255) / 256;
+    dim3 grid((d + 255) / 256, chunks);
+    hot_sum_kernel<<<grid, 256, 0, STREAM>>>(ids, (const bf16*)d_emb, scale, d_table, M, d, hot_id, 256);
+    MIC_CHECK_LAUNCH();
+  }
   if (d_pos_rows) {
     dim3 grid(T, (d + 255) / 256);
     batch_sum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)d_emb, B, T, d, d_pos_rows, d);

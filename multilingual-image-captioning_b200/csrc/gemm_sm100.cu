@@ -140,12 +140,12 @@ static int launch_one(cudaStream_t stream, const Operands& o, const typename Epi
   auto kern = gemm_kernel<A_MN, B_MN, BN, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
-    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks * o.shape.split_k;
   const int grid = tiles < mic_num_sms() ? tiles : mic_num_sms();
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.td, o.td2, o.shape, ep);
+  kern<<<grid, Cfg<BN, Epi::NBUF, Epi::EW>::THREADS, Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.td, o.td2, o.shape, ep);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
@@ -234,6 +234,8 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
       ep.accumulate = 1;
     }
   }
+  if (!a_mn_major && b_mn_major && act != MIC_ACT_NONE && tma && o.bn == 256)
+    return launch_one<0, 1, 256, EpiStoreAct16>(s, o, ep);
   if (!a_mn_major && b_mn_major) return launch_bn<0, 1, EpiStore>(s, o, ep);
   if (!a_mn_major && !b_mn_major) return launch_bn<0, 0, EpiStore>(s, o, ep);
   if (a_mn_major && b_mn_major) return launch_bn<1, 1, EpiStore>(s, o, ep);

@@ -23,23 +23,29 @@ namespace micgemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;           // default; activation-heavy epilogues use 16 (Epi::EW)
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int GROUP_COLS = 64;          // epilogue granularity: 64 accumulator columns
 constexpr int STG_BYTES = 4096;         // per-warp staging: 32 rows x 128 B
 
-template <int BN>
+template <int BN, int NBUF = 1, int EW = NUM_EPI_WARPS>
 struct Cfg {
   static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported BLOCK_N");
+  static_assert(NBUF == 1 || NBUF == 2, "one or two staging buffers per epilogue warp");
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * STG_BYTES;
+  // smem budget 227 KB: mainloop stages + NBUF x 32 KB of epilogue staging
+  static constexpr int EPI_BYTES = EW * STG_BYTES * NBUF;
+  static constexpr int STAGES_WANTED = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGES_FIT = (232448 - 1280 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_WANTED < STAGES_FIT ? STAGES_WANTED : STAGES_FIT;
+  static constexpr int THREADS = 128 + EW * 32;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int NUM_GROUPS = BN / GROUP_COLS;
   static constexpr int GROUPS_HALF0 = (NUM_GROUPS + 1) / 2;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
 struct Shape {
@@ -79,8 +85,14 @@ struct EpiCtx {
 __device__ __forceinline__ uint8_t* stg_addr(uint8_t* stg, int r, int u) { return stg + r * 128 + ((u ^ (r & 7)) << 4); }
 
 // make the staging buffer writable again: the issuing lane waits until earlier TMA stores have read it
+template <int PENDING = 0>
 __device__ __forceinline__ void stg_acquire(int lane) {
-  if (lane == 0) tma_store_wait_read();
+  if (lane == 0) {
+    if (PENDING == 0)
+      tma_store_wait_read();
+    else
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the newest store may still be reading
+  }
   __syncwarp();
 }
 // publish the staging buffer (written with st.shared by all lanes) through a TMA store
@@ -114,7 +126,12 @@ struct EpiStoreParams {
   DropoutParams drop;   // dropout on the activation output, before the residual add (flax: x + dropout(f(x)))
 };
 
-struct EpiStore {
+// NBUF = 2: a second staging buffer per warp carries the pre-activation copy (D2), so the two outputs of a
+// group alternate buffers and never wait on each other's TMA read (used for the fc1 GEMMs of training).
+template <int NBUF_, int EW_ = NUM_EPI_WARPS>
+struct EpiStoreT {
+  static constexpr int NBUF = NBUF_;
+  static constexpr int EW = EW_;
   typedef EpiStoreParams Params;
   struct State {};
   __device__ static void kernel_begin(const Params&, State&) {}
@@ -162,7 +179,7 @@ struct EpiStore {
     // ---- residual tile: coalesced 16-byte loads -> swizzled staging -> registers ----
     uint4 res[8];
     if (p.residual) {
-      stg_acquire(lane);
+      stg_acquire<0>(lane);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + (lane >> 3), u = lane & 7;
@@ -192,9 +209,23 @@ struct EpiStore {
       x[6] = x[6] * p.out_scale + b1.z; x[7] = x[7] * p.out_scale + b1.w;
     }
     // ---- optional pre-activation copy ----
-    if (p.D2) {
-      // direct row-per-thread stores: keeps the single staging buffer free for the main output, so the
-      // two outputs of a group never wait on each other's TMA read (the LSU has slack here)
+    if (p.D2 && (NBUF == 2 || EW == 16)) {
+      // staged TMA store of the copy: into the second buffer (NBUF == 2), or — with 16 epilogue warps, one
+      // group per warp and tile — into the single buffer, whose read finishes during the activation math
+      uint8_t* stg2 = NBUF == 2 ? stg + STG_BYTES : stg;
+      if (NBUF == 2)
+        stg_acquire<1>(lane);
+      else
+        stg_acquire<0>(lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* x = v + u * 8;
+        *reinterpret_cast<uint4*>(stg_addr(stg2, lane, u)) =
+            make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      }
+      stg_store(ctx.tmap_d2, stg2, lane, col0, ctx.row0, false);
+    } else if (p.D2) {
+      // single staging buffer: direct row-per-thread stores for the copy
       if (ctx.row < s.M) {
         bf16* d2 = p.D2 + (long long)ctx.row * p.ldd + col0;
 #pragma unroll
@@ -233,7 +264,10 @@ struct EpiStore {
       }
     }
     if (!p.d_f32) {
-      stg_acquire(lane);
+      if (NBUF == 2 && p.D2)
+        stg_acquire<1>(lane);
+      else
+        stg_acquire<0>(lane);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float* x = v + u * 8;
@@ -246,7 +280,7 @@ struct EpiStore {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         if (col0 + hh * 32 >= s.N) break;        // warp-uniform
-        stg_acquire(lane);
+        stg_acquire<0>(lane);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const float* x = v + hh * 32 + u * 4;
@@ -257,6 +291,9 @@ struct EpiStore {
     }
   }
 };
+typedef EpiStoreT<1> EpiStore;
+typedef EpiStoreT<2> EpiStoreDual;
+typedef EpiStoreT<1, 16> EpiStoreAct16;      // 16 epilogue warps: GELU / quick-GELU epilogues are issue bound
 
 // --------------------------------------------------------------------------------------------
 // Epilogue policy 1: lm_head + log-softmax / label-smoothed CE statistics (no logits written)
@@ -275,6 +312,8 @@ struct EpiCEStatsParams {
 
 struct EpiCEStats {
   typedef EpiCEStatsParams Params;
+  static constexpr int NBUF = 1;
+  static constexpr int EW = NUM_EPI_WARPS;
   struct State {
     float mx, sm, sz;
     int label;
@@ -353,6 +392,8 @@ struct EpiCEGradParams {
 
 struct EpiCEGrad {
   typedef EpiCEGradParams Params;
+  static constexpr int NBUF = 1;
+  static constexpr int EW = NUM_EPI_WARPS;
   struct State {
     float lse2, w;
     int label;
@@ -397,7 +438,7 @@ struct EpiCEGrad {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] += (rel == static_cast<unsigned>(j)) ? fix : 0.f;
     }
-    stg_acquire(ctx.lane);
+    stg_acquire<0>(ctx.lane);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float* x = v + u * 8;
@@ -429,6 +470,8 @@ struct EpiSearchParams {
 // in registers across the whole kernel and are written once (partial slot = CTA rank within the m-block).
 struct EpiSearch {
   typedef EpiSearchParams Params;
+  static constexpr int NBUF = 1;
+  static constexpr int EW = NUM_EPI_WARPS;
   struct State {
     float mx, sm;
     float tv[SEARCH_TOPK];
@@ -520,11 +563,11 @@ struct EpiSearch {
 // The kernel
 // --------------------------------------------------------------------------------------------
 template <int A_MN, int B_MN, int BN, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(128 + Epi::EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d2,
             const Shape shape, const typename Epi::Params ep) {
-  typedef Cfg<BN> C;
+  typedef Cfg<BN, Epi::NBUF, Epi::EW> C;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // 1024B alignment for SWIZZLE_128B
@@ -555,7 +598,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], Epi::EW);
     }
     fence_barrier_init();
   }
@@ -646,12 +689,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - 4;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;           // which share of the tile's 64-column groups
-    const int g_begin = half == 0 ? 0 : C::GROUPS_HALF0;
-    const int g_end = half == 0 ? C::GROUPS_HALF0 : C::NUM_GROUPS;
+    const int half = ew >> 2;           // which share of the tile's 64-column groups (Epi::EW / 4 shares)
+    constexpr int kShares = Epi::EW / 4;
+    const int g_begin = kShares == 2 ? (half == 0 ? 0 : C::GROUPS_HALF0) : (half * C::NUM_GROUPS) / kShares;
+    const int g_end = kShares == 2 ? (half == 0 ? C::GROUPS_HALF0 : C::NUM_GROUPS) : ((half + 1) * C::NUM_GROUPS) / kShares;
     EpiCtx ctx;
     ctx.lane = lane;
-    ctx.stg = smem_epi + ew * STG_BYTES;
+    ctx.stg = smem_epi + ew * STG_BYTES * Epi::NBUF;
     ctx.tmap_d = &tmap_d;
     ctx.tmap_d2 = &tmap_d2;
     uint32_t it = 0;

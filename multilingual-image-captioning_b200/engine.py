@@ -318,9 +318,9 @@ class CaptionEngine:
         gpos = ps.g("d.pos")
         gpos.zero_()
         if pos is None:
-            ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), gpos[t.position_offset:], B, T)
+            ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), gpos[t.position_offset:], B, T, t.pad_token_id)
         else:
-            ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), None, B, T)
+            ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), None, B, T, t.pad_token_id)
             gpos.index_add_(0, (pos + t.position_offset).long(), demb.float())   # rare path (explicit position ids)
         # ---------------- backward: cross K/V projection ----------------
         d_enc = b.get("tr.d_enc", (Mv, d))

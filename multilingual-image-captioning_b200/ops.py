@@ -187,9 +187,9 @@ def embed_ln_fwd(ids, pos_ids, pos_mod, pos_offset, table, pos_table, scale, gam
     return out
 
 
-def embed_bwd(ids, d_emb, scale, d_table, d_pos_rows, B, T):
+def embed_bwd(ids, d_emb, scale, d_table, d_pos_rows, B, T, hot_id=-1):
     d = d_emb.shape[-1]
-    _call("mic_embed_bwd", _p(ids), _p(d_emb), float(scale), _p(d_table), _p(d_pos_rows), B, T, d)
+    _call("mic_embed_bwd", _p(ids), _p(d_emb), float(scale), _p(d_table), _p(d_pos_rows), B, T, d, int(hot_id))
 
 
 def batch_sum(x, B, T, d, out, out_ld):

@@ -193,7 +193,7 @@ def test_embed_fwd_bwd():
     d_emb = rnd(B * T, d, seed=42)
     d_table = torch.zeros(V, d, device=DEV)
     d_pos = torch.zeros(T + 2, d, device=DEV)
-    ops.embed_bwd(ids, d_emb, scale, d_table, d_pos[2:], B, T)
+    ops.embed_bwd(ids, d_emb, scale, d_table, d_pos[2:], B, T, hot_id=1)
     torch.cuda.synchronize()
     want = torch.zeros(V, d, device=DEV).index_add_(0, ids.long(), d_emb.float() * scale)
     close(d_table, want, 1e-3, 1e-4, "d_table")
