@@ -34,6 +34,20 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the CE-stats GEMM from the committed `ncu --set full` summary."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_cestats.txt")
+    if not os.path.exists(p):
+        return None
+    tot = 0.0
+    for line in open(p):
+        for key in ("dram__bytes_read.sum =", "dram__bytes_write.sum ="):
+            if key in line:
+                val, unit = line.split("=")[1].split()[:2]
+                tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+    return tot or None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -234,7 +248,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<K,K,256,EpiCEStats> (tied lm_head + log-softmax/CE stats)",
                      "achieved": k_tflops, "peak": peak_sus, "unit": "TFLOP/s", "frac": k_tflops / peak_sus,
-                     "peak_source": f"{peak_src} (sustained: kernel timed inside a long step)", "traffic": None,
+                     "peak_source": f"{peak_src} (sustained: kernel timed inside a long step)", "traffic": ncu_traffic_bytes(),
                      "kernel_ms": k_ms, "flops_per_launch": k_flops},
         "step_roofline": {"achieved": step_tflops, "peak": peak_sus, "unit": "TFLOP/s", "frac": step_tflops / peak_sus,
                           "flop_per_sample": FLOP_PER_SAMPLE},

@@ -52,12 +52,20 @@ int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const void* A, l
 int mic_lm_head_num_partials(int vocab);
 int mic_lm_head_ce_stats(void* stream, const void* H, long long ldh, const void* E, long long lde,
                          const float* bias, const int* labels, int M, int V, int K, float* pmax, float* psum,
-                         float* psumz, float* zlabel);
+                         float* psumz, float* zlabel, void* logits_out /* optional bf16 [M, ldl] */, long long ldl);
 /* finalize: lse[M], per-row loss, row_w = mask/sum(mask), out[0] = loss, out[1] = sum(mask) */
 int mic_ce_finalize(void* stream, const float* pmax, const float* psum, const float* psumz, const float* zlabel,
                     const int* mask, int num_partials, int M, int V, float label_smoothing, float* lse,
                     float* row_loss, float* row_w, float* out);
-/* backward [L2]: dlogits = (softmax - soft_labels) * row_w, bf16 [M, ldd], ldd % 256 == 0, pad cols = 0 */
+/* backward [L2], no recompute: rewrites the bf16 logits left by mic_lm_head_ce_stats IN PLACE as
+ * dlogits = (softmax - soft_labels) * row_w (columns >= V -> 0) and writes dbias[V] = column sums
+ * (gradient of final_logits_bias).  workspace: mic_ce_softmax_bwd_workspace_floats; counters as below. */
+long long mic_ce_softmax_bwd_workspace_floats(int M, long long ld);
+int mic_ce_softmax_bwd(void* stream, void* logits_inout, long long ld, const int* labels, const float* lse,
+                       const float* row_w, float conf, float low, int M, int V, float* dbias, float* workspace,
+                       unsigned int* counters);
+/* backward [L2], recompute variant (no stored logits): dlogits = (softmax - soft_labels) * row_w, bf16 [M, ldd],
+ * ldd % 256 == 0, pad cols = 0 */
 int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, const void* E, long long lde,
                         const float* bias, const int* labels, const float* lse, const float* row_w, float conf,
                         float low, int M, int V, int K, void* dlogits, long long ldd);

@@ -20,7 +20,9 @@ SIGNATURES = {
     "mic_abi_version": [],
     "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I, P, I, F],
     "mic_lm_head_num_partials": [I],
-    "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P],
+    "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P, P, L],
+    "mic_ce_softmax_bwd_workspace_floats": [I, L],
+    "mic_ce_softmax_bwd": [P, P, L, P, P, P, F, F, I, I, P, P, P],
     "mic_ce_finalize": [P, P, P, P, P, P, I, I, I, F, P, P, P, P],
     "mic_lm_head_ce_grad": [P, P, L, P, L, P, P, P, P, F, F, I, I, I, P, L],
     "mic_lm_head_search_num_partials": [I],

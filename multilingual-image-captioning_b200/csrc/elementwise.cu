@@ -331,6 +331,67 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// CE backward without recomputing the lm_head: the forward kernel left the bf16 logits z in `zdz`
+// [M, ld]; this pass rewrites them IN PLACE as dlogits = (softmax(z) - soft_labels) * row_w and, in the
+// same sweep, accumulates the column sums (= gradient of final_logits_bias).  Columns >= V become 0.
+// grid = (ld/256, row chunks); block 256 = 32 column groups (8 cols) x 8 row lanes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ce_softmax_bwd_kernel(bf16* __restrict__ zdz, long long ld, const int* __restrict__ labels,
+                      const float* __restrict__ lse, const float* __restrict__ row_w, float conf, float low, int M,
+                      int V, float* __restrict__ part, unsigned int* __restrict__ counters,
+                      float* __restrict__ dbias, int rows_per_chunk) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r = r0 + rl; r < r1; r += 8) {
+    bf16* p = zdz + (long long)r * ld + c;
+    float z[8];
+    load8(p, z);
+    const float w = row_w[r];
+    const float l2 = lse[r] * 1.4426950408889634f;
+    const int rel = labels[r] - c;
+    const float lw = low * w, fix = (low - conf) * w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = fmaf(exp2f(fmaf(z[j], 1.4426950408889634f, -l2)), w, -lw);
+      d += (rel == j) ? fix : 0.f;
+      d = (c + j < V) ? d : 0.f;
+      z[j] = bf16_round(d);
+      acc[j] += z[j];
+    }
+    store8(p, z);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int col = blockIdx.x * 256 + t;
+  const int nch = gridDim.y;
+  {
+    float sum = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][t];
+    part[(long long)blockIdx.y * ld + col] = sum;
+  }
+  if (last_cta_of_column(counters + blockIdx.x, nch) && col < V) {
+    float s0 = 0.f, s1 = 0.f;
+    int pch = 0;
+    for (; pch + 1 < nch; pch += 2) {
+      s0 += part[(long long)pch * ld + col];
+      s1 += part[(long long)(pch + 1) * ld + col];
+    }
+    if (pch < nch) s0 += part[(long long)pch * ld + col];
+    dbias[col] = s0 + s1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Decoder embedding: shared[id]*scale + positions[pos+offset] -> emb (bf16) -> LayerNorm -> y
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -759,6 +820,24 @@ extern "C" int mic_act_bwd_colsum(void* stream, const void* dY, long long ldy, c
   act_bwd_colsum_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)dY, ldy, (const bf16*)U, ldu, act, (bf16*)dU, lddu,
                                                   workspace, counters, dbias, accumulate, M, N,
                                                   (M + chunks - 1) / chunks, drop);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+static int ce_bwd_chunks(int M) {
+  int ch = (M + 511) / 512;
+  return ch < 1 ? 1 : ch;
+}
+extern "C" long long mic_ce_softmax_bwd_workspace_floats(int M, long long ld) { return (long long)ce_bwd_chunks(M) * ld; }
+
+extern "C" int mic_ce_softmax_bwd(void* stream, void* logits_inout, long long ld, const int* labels, const float* lse,
+                                  const float* row_w, float conf, float low, int M, int V, float* dbias,
+                                  float* workspace, unsigned int* counters) {
+  MIC_CHECK_ARG(ld % 256 == 0 && ld >= V && ld / 256 <= 1024, "ce_softmax_bwd: ld=%lld must be a multiple of 256, >= V", ld);
+  const int chunks = ce_bwd_chunks(M);
+  dim3 grid((unsigned)(ld / 256), chunks);
+  ce_softmax_bwd_kernel<<<grid, 256, 0, STREAM>>>((bf16*)logits_inout, ld, labels, lse, row_w, conf, low, M, V,
+                                                  workspace, counters, dbias, (M + chunks - 1) / chunks);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

@@ -250,11 +250,16 @@ extern "C" int mic_lm_head_num_partials(int vocab) { return 2 * ((vocab + 255) /
 
 extern "C" int mic_lm_head_ce_stats(void* stream, const void* H, long long ldh, const void* E, long long lde,
                                     const float* bias, const int* labels, int M, int V, int K, float* pmax,
-                                    float* psum, float* psumz, float* zlabel) {
+                                    float* psum, float* psumz, float* zlabel, void* logits_out, long long ldl) {
   Operands o;
   int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, (M + BLOCK_M - 1) / BLOCK_M);
   if (rc) return rc;
-  EpiCEStatsParams ep = {bias, labels, pmax, psum, psumz, zlabel};
+  EpiCEStatsParams ep = {bias, labels, pmax, psum, psumz, zlabel, logits_out ? 1 : 0};
+  if (logits_out) {
+    MIC_CHECK_ARG(ldl % 256 == 0 && ldl >= V, "logits leading dimension %lld must be a multiple of 256 >= V", ldl);
+    rc = mic_make_tmap_2d(&o.td, logits_out, 2, ldl, M, ldl, 64, 32);
+    if (rc) return rc;
+  }
   return launch_one<0, 0, 256, EpiCEStats>(reinterpret_cast<cudaStream_t>(stream), o, ep);
 }
 

@@ -306,6 +306,7 @@ struct EpiCEStatsParams {
   float* psum;           // [2*num_n_blocks, M]
   float* psumz;          // [2*num_n_blocks, M]
   float* zlabel;         // [M]
+  int store_logits;      // 1: also emit the (bias-added) logits as bf16 through tmap_d (backward reuses them)
 };
 
 #define MIC_LOG2E 1.4426950408889634f
@@ -366,6 +367,16 @@ struct EpiCEStats {
     for (int j = 0; j < 64; ++j) acc += exp2f(fmaf(v[j], MIC_LOG2E, -nm2));
     st.sm = st.sm * exp2f((st.mx - nm) * MIC_LOG2E) + acc;
     st.mx = nm;
+    if (p.store_logits) {
+      stg_acquire<0>(ctx.lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* x = v + u * 8;
+        *reinterpret_cast<uint4*>(stg_addr(ctx.stg, ctx.lane, u)) =
+            make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      }
+      stg_store(ctx.tmap_d, ctx.stg, ctx.lane, col0, ctx.row0, false);
+    }
   }
   __device__ static void tile_end(const Params& p, State& st, const Shape& s, int row, int, int n_blk, int half) {
     if (row >= s.M) return;

@@ -54,6 +54,36 @@ class CaptionEngine:
         # decoder dropout (flax.linen.Dropout, rate = mbart_config.dropout) — active only inside train steps
         self.dropout_p = 0.0
         self.drop_seed = torch.zeros(1, dtype=I32, device=self.dev)
+        # weight-gradient GEMMs run on a side stream (a parallel branch of the captured graph): their
+        # prologue / last partial wave overlaps the data-gradient GEMM that follows on the main stream
+        self.overlap_wgrad = True
+        self._side = None
+        self._side_bufs = set()      # data_ptr of every buffer outstanding side-stream work reads or writes
+
+    def _fork_side(self, fn, *buffers):
+        if not self.overlap_wgrad:
+            fn()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn()
+        for t in buffers:
+            self._side_bufs.add(t.data_ptr())
+
+    def _before_write(self, *tensors):
+        """Main-stream kernels that overwrite a buffer still used by side-stream work must wait for it."""
+        if self._side_bufs and any(t is not None and t.data_ptr() in self._side_bufs for t in tensors):
+            self._join_side()
+
+    def _join_side(self):
+        if self._side is not None and self._side_bufs:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_bufs.clear()
 
     def _drop(self, site):
         """(seed tensor, site key, p) for dropout site `site` of this step, or None when dropout is off."""
@@ -75,6 +105,7 @@ class CaptionEngine:
     def _ln_bwd(self, dy, x, name, stats, dres, dx):
         ps = self.ps
         d = x.shape[1]
+        self._before_write(dx)
         ws = self._workspace(max(ops.ln_bwd_workspace_floats(x.shape[0], d), 1))
         ops.layernorm_bwd(dy, x, ps.f(name + ".scale"), stats[0], stats[1], dres, dx, ps.g(name + ".scale"),
                           ps.g(name + ".bias"), ws)
@@ -93,15 +124,19 @@ class CaptionEngine:
         if dropout is not None:
             # y = residual + dropout(x W + b): the gradient reaching this Dense is dy * mask / (1-p)
             du = self.bufs.get("tr.dmask", tuple(dy.shape))
+            self._before_write(du)
             ops.act_bwd_colsum(dy, None, "none", du, gb, ws, dropout=dropout)
             dy = du
         elif act is not None and act != "none":
+            self._before_write(du)
             ops.act_bwd_colsum(dy, u, act, du, gb, ws)
             dy = du
         elif gb is not None:
             ops.act_bwd_colsum(dy, None, "none", None, gb, ws)
-        ops.gemm(x, dy, a_mn=True, b_mn=True, out=gw)                       # dW[K,N] = x^T dy
+        dyv = dy
+        self._fork_side(lambda: ops.gemm(x, dyv, a_mn=True, b_mn=True, out=gw), x, dyv, gw)   # dW[K,N] = x^T dy
         if dx_out is not None:
+            self._before_write(dx_out)
             ops.gemm(dy, w, a_mn=False, b_mn=False, out=dx_out)               # dx[M,K] = dy W^T
         return dx_out
 
@@ -216,11 +251,11 @@ class CaptionEngine:
                 "zlabel": f("zlabel", M), "lse": f("lse", M), "row_loss": f("row_loss", M), "row_w": f("row_w", M),
                 "out": f("out", 2)}
 
-    def loss_forward(self, hf, labels, mask, label_smoothing):
+    def loss_forward(self, hf, labels, mask, label_smoothing, logits_out=None):
         ps, V = self.ps, self.t.vocab_size
         M = hf.shape[0]
         ws = self._ce_ws(M)
-        ops.lm_head_ce_stats(hf, ps.w("shared"), ps.f("flb"), labels, ws)
+        ops.lm_head_ce_stats(hf, ps.w("shared"), ps.f("flb"), labels, ws, logits_out)
         ops.ce_finalize(ws, mask, M, V, label_smoothing)
         return ws
 
@@ -254,17 +289,18 @@ class CaptionEngine:
         enc = self.encode(pixel_values, trunc_int=False, save=True, tag="tr.enc")
         enc_kv = self.cross_kv(enc, tag="tr.enc")
         hf = self.decoder_forward(ids, km, pos, enc_kv, B, T, S, save=True, tag="tr.dec", train=True)
-        ws = self.loss_forward(hf, lab, km.view(-1), label_smoothing)
+        # the forward CE kernel also leaves the bf16 logits (what the reference's bf16 mode materialises) in
+        # the buffer that backward turns into dlogits in place: no lm_head recompute
+        dlog = b.get("tr.dlogits", (M, self.Vp))
+        ws = self.loss_forward(hf, lab, km.view(-1), label_smoothing, logits_out=dlog)
         # ---------------- backward: lm_head + CE ----------------
         V = t.vocab_size
         conf, low = 1.0 - label_smoothing, label_smoothing / (V - 1)
-        dlog = b.get("tr.dlogits", (M, self.Vp))
-        ops.lm_head_ce_grad(hf, ps.w("shared"), ps.f("flb"), lab, ws, conf, low, dlog)
-        cws = self._workspace(ops.colsum_workspace_floats(M, self.Vp))
-        flb_pad = b.get("tr.dflb", (self.Vp,), F32)
-        ops.act_bwd_colsum(dlog, None, "none", None, flb_pad, cws)
-        ps.g("flb").copy_(flb_pad[:V])
-        ops.gemm(dlog[:, :V], hf, a_mn=True, b_mn=True, out=ps.g("shared"))          # dE = dlogits^T h
+        cws = self._workspace(ops.ce_softmax_bwd_workspace_floats(M, self.Vp))
+        ops.ce_softmax_bwd(dlog, lab, ws, conf, low, V, ps.g("flb"), cws)
+        gshared = ps.g("shared")
+        dlv = dlog[:, :V]
+        self._fork_side(lambda: ops.gemm(dlv, hf, a_mn=True, b_mn=True, out=gshared), dlog, hf, gshared)   # dE = dlogits^T h
         dx = b.get("tr.dx", (M, d))
         dhf = ops.gemm(dlog[:, :V], ps.w("shared"), a_mn=False, b_mn=True, out=b.get("tr.dhf", (M, d)))
         tg = "tr.dec"
@@ -296,6 +332,7 @@ class CaptionEngine:
             self._dense_bwd(ca, dx, n + ".ca_o", dtmp, dropout=self._drop(11 + 4 * l))
             kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
             vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+            self._before_write(dqc, d_enc_kv)
             ops.attention_bwd(qc, kl, vl, ca, dtmp, b.t[tg + ".lse2" + sfx], None, False, dqc,
                               d_enc_kv[:, l * 2 * d: l * 2 * d + d], d_enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d],
                               B, H, T, S, scale)
@@ -304,6 +341,7 @@ class CaptionEngine:
             # self attention
             sa, qkv, lnA = b.t[tg + ".sa" + sfx], b.t[tg + ".qkv" + sfx], b.t[tg + ".lnA" + sfx]
             self._dense_bwd(sa, dx, n + ".sa_o", dtmp, dropout=self._drop(10 + 4 * l))
+            self._before_write(dqkv)
             ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, dtmp, b.t[tg + ".lse1" + sfx], km, True,
                               dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, T, T, scale)
             self._dense_bwd(lnA, dqkv, n + ".sa_qkv", dtmp)
@@ -311,12 +349,14 @@ class CaptionEngine:
         # embedding
         if self._drop(1) is not None:       # dropout after layernorm_embedding
             dmask = b.get("tr.dmask", (M, d))
+            self._before_write(dmask)
             ops.act_bwd_colsum(dx, None, "none", dmask, None, self._workspace(ops.colsum_workspace_floats(M, d)),
                                dropout=self._drop(1))
             dx = dmask
         demb = self._ln_bwd(dx, b.t[tg + ".emb"], "d.ln_emb", (b.t[tg + ".emb.mean"], b.t[tg + ".emb.rstd"]), None, dtmp)
         gpos = ps.g("d.pos")
         gpos.zero_()
+        self._before_write(ps.g("shared"))          # the lm_head wgrad must have landed before the scatter-add
         if pos is None:
             ops.embed_bwd(ids, demb, self.emb_scale, ps.g("shared"), gpos[t.position_offset:], B, T, t.pad_token_id)
         else:
@@ -326,6 +366,7 @@ class CaptionEngine:
         d_enc = b.get("tr.d_enc", (Mv, d))
         self._dense_bwd(enc, d_enc_kv, "d.ca_kv", d_enc)
         if stage == 1:
+            self._join_side()
             return ws
         self._backward_vision(B, S, Mv, dv, d)
         return ws
@@ -367,6 +408,7 @@ class CaptionEngine:
             self._ln_bwd(dvt, xm, n + ".ln2", (b.t[te + ".ln2.mean" + sfx], b.t[te + ".ln2.rstd" + sfx]), dxv, dxv)
             att, qkv, ln1 = b.t[te + ".att" + sfx], b.t[te + ".qkv" + sfx], b.t[te + ".ln1" + sfx]
             self._dense_bwd(att, dxv, n + ".o", dvt)
+            self._before_write(dqkvv)
             ops.attention_bwd(qkv[:, :dv], qkv[:, dv:2 * dv], qkv[:, 2 * dv:], att, dvt, b.t[te + ".lse" + sfx], None,
                               False, dqkvv[:, :dv], dqkvv[:, dv:2 * dv], dqkvv[:, 2 * dv:], B, Hv, S, S, vscale)
             self._dense_bwd(ln1, dqkvv, n + ".qkv", dvt)
@@ -381,8 +423,11 @@ class CaptionEngine:
             ps.g("v.pre_ln.bias").zero_()
         ops.batch_sum(demb_v, B, S, dv, ps.g("v.pos"), dv)
         ps.g("v.cls").copy_(ps.g("v.pos")[0])
-        dpo = ops.drop_cls_rows(demb_v, b.get("tr.dpo", (B * (S - 1), dv)), B, S)
+        dpo = b.get("tr.dpo", (B * (S - 1), dv))
+        self._before_write(dpo)
+        ops.drop_cls_rows(demb_v, dpo, B, S)
         if c.patch_bias:
             ops.act_bwd_colsum(dpo, None, "none", None, ps.g("v.patch.b"), self._workspace(
                 ops.colsum_workspace_floats(dpo.shape[0], dv)))
         ops.gemm(b.t[te + ".patches"], dpo, a_mn=True, b_mn=True, out=ps.g("v.patch.w"))
+        self._join_side()

@@ -93,11 +93,22 @@ def lm_head_search_num_partials(M):
     return lib().mic_lm_head_search_num_partials(M)
 
 
-def lm_head_ce_stats(h, emb, bias, labels, ws):
+def lm_head_ce_stats(h, emb, bias, labels, ws, logits_out=None):
     M, K = h.shape
     V = emb.shape[0]
     _call("mic_lm_head_ce_stats", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), _p(labels), M, V, K, _p(ws["pmax"]),
-          _p(ws["psum"]), _p(ws["psumz"]), _p(ws["zlabel"]))
+          _p(ws["psum"]), _p(ws["psumz"]), _p(ws["zlabel"]), _p(logits_out),
+          _ld(logits_out) if logits_out is not None else 0)
+
+
+def ce_softmax_bwd_workspace_floats(M, ld):
+    return lib().mic_ce_softmax_bwd_workspace_floats(M, ld)
+
+
+def ce_softmax_bwd(logits_inout, labels, ws, conf, low, V, dbias, workspace):
+    M = logits_inout.shape[0]
+    _call("mic_ce_softmax_bwd", _p(logits_inout), _ld(logits_inout), _p(labels), _p(ws["lse"]), _p(ws["row_w"]),
+          float(conf), float(low), M, V, _p(dbias), _p(workspace), _p(counters(logits_inout.device)))
 
 
 def ce_finalize(ws, mask, M, V, label_smoothing, with_loss=True):

@@ -403,3 +403,37 @@ def test_dropout_mask_is_shared_by_forward_and_backward():
     out2 = ops.gemm(a, w, b_mn=True, residual=res, dropout=(seed, 78, p))
     torch.cuda.synchronize()
     assert (out2 != out).float().mean().item() > 0.1
+
+
+@pytest.mark.parametrize("V,M,eps", [(1003, 200, 0.1), (5000, 300, 0.0)])
+def test_ce_backward_from_stored_logits(V, M, eps):
+    """Forward stores bf16 logits; backward rewrites them in place as dlogits and emits the bias gradient."""
+    K = 128
+    h = rnd(M, K, seed=11)
+    E = rnd(V, K, seed=12, scale=0.2)
+    bias = rnd(V, seed=13, dtype=torch.float32, scale=0.1)
+    g = torch.Generator().manual_seed(14)
+    labels = torch.randint(0, V, (M,), generator=g, dtype=torch.int32).to(DEV)
+    mask = (torch.rand(M, generator=g) > 0.3).to(torch.int32).to(DEV)
+    mask[0] = 1
+    ws = _ce_ws(M, V)
+    Vp = (V + 255) // 256 * 256
+    buf = torch.full((M, Vp), float("nan"), dtype=BF16, device=DEV)
+    ops.lm_head_ce_stats(h, E, bias, labels, ws, logits_out=buf)
+    ops.ce_finalize(ws, mask, M, V, eps)
+    torch.cuda.synchronize()
+    z = (h.float() @ E.float().t() + bias)
+    close(buf[:, :V], z, 3e-2, 1e-2, "stored logits")
+    conf, low = 1.0 - eps, eps / (V - 1)
+    dbias = torch.full((V,), 9.0, device=DEV)
+    wsp = torch.zeros(ops.ce_softmax_bwd_workspace_floats(M, Vp), device=DEV)
+    ops.ce_softmax_bwd(buf, labels, ws, conf, low, V, dbias, wsp)
+    torch.cuda.synchronize()
+    zz = z.clone().requires_grad_(True)
+    lsm = torch.log_softmax(zz, -1)
+    soft = torch.full_like(zz, low).scatter_(1, labels.long()[:, None], conf)
+    loss = ((-(soft * lsm).sum(-1)) * mask.float()).sum() / mask.float().sum()
+    loss.backward()
+    close(buf[:, :V], zz.grad, 3e-5, 6e-2, "dlogits from stored logits")
+    assert float(buf[:, V:].float().abs().max()) == 0.0
+    close(dbias, buf[:, :V].float().sum(0), 2e-4, 1e-3, "final_logits_bias gradient")
