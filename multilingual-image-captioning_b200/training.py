@@ -97,13 +97,18 @@ class TrainState:
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
             bucketed_allreduce_sum(g[lo:hi], self.bucket_elems)
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        return done
 
     def wait_comm(self):
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
-    def apply_gradients(self):
-        """optax.adamw with the schedule evaluated at the pre-increment count."""
+    def apply_gradients(self, segments=None):
+        """optax.adamw with the schedule evaluated at the pre-increment count.
+        segments: optional [(lo, hi, event)] — AdamW runs slice by slice, each after its all-reduce event, so the
+        optimiser of the first bucket overlaps the communication of the second."""
         count = self.step
         t = count + 1
         lr = float(self.learning_rate_fn(count))
@@ -117,7 +122,14 @@ class TrainState:
         self.hp_host[7] = 1.0 / self.world
         self.hp_dev.copy_(self.hp_host, non_blocking=True)
         s = self.store
-        ops.adamw(s.master, s.adam_m, s.adam_v, s.grad, s.shadow, self.hp_dev)
+        if segments is None:
+            ops.adamw(s.master, s.adam_m, s.adam_v, s.grad, s.shadow, self.hp_dev)
+        else:
+            cur = torch.cuda.current_stream()
+            for lo, hi, ev in segments:
+                if ev is not None:
+                    cur.wait_event(ev)
+                ops.adamw(s.master[lo:hi], s.adam_m[lo:hi], s.adam_v[lo:hi], s.grad[lo:hi], s.shadow[lo:hi], self.hp_dev)
         self.step = t
         return lr
 
@@ -194,11 +206,13 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
     def run_stage(stage):
         return eng.forward_backward(*args, label_smoothing=label_smoothing_factor, stage=stage)
 
+    evs = []
+
     def between():
         # lax.pmean of everything produced so far (lm_head bias, tied embedding, decoder, cross K/V = 84 % of
         # the bytes) on the communication stream while the vision backward keeps the SMs busy
         if dp:
-            state.allreduce_grads(0, eng.grad_split_offset(), async_stream=True)
+            evs.append(state.allreduce_grads(0, eng.grad_split_offset(), async_stream=True))
 
     if not use_cuda_graph:
         ws = None
@@ -239,9 +253,11 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
                 between()
         ws = sb["ws"]
     if dp:
-        state.allreduce_grads(eng.grad_split_offset(), None, async_stream=True)
-        state.wait_comm()
-    lr = state.apply_gradients()
+        split, n = eng.grad_split_offset(), state.store.grad.numel()
+        ev2 = state.allreduce_grads(split, None, async_stream=True)
+        lr = state.apply_gradients([(0, split, evs[-1]), (split, n, ev2)])
+    else:
+        lr = state.apply_gradients()
     loss = ws["out"][0:1].clone()
     if state.world > 1:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM)
