@@ -147,7 +147,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     peaks, peak_src = load_peaks()
 
-    cfg = mic_b200.clip_mbart_config()
+    vit_bart = args.model == "vit-bart"
+    cfg = mic_b200.vit_bart_config() if vit_bart else mic_b200.clip_mbart_config()
+    flop_per_sample = 225.93e9 if vit_bart else FLOP_PER_SAMPLE
+    wl_name = ("ViT-B/16 + BART-large (flax_vit_bart variant, 197 visual tokens)" if vit_bart
+               else "CLIP-ViT-B/32 + mBART-50") + " training step (fwd+bwd+AdamW), 224x224 images, 64-token captions"
     B, T = args.batch, 64
     model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, seed=0, device=dev)
     sched = mic_b200.create_learning_rate_fn(10_000_000, B * world, 7, 1000, 5e-5)
@@ -234,13 +238,12 @@ def run_ours(args):
     k_tflops = k_flops / (k_ms / 1e3) / 1e12
     peak_burst = peaks["bf16_tflops"]
     peak_sus = peaks.get("bf16_tflops_sustained", peak_burst)
-    step_tflops = FLOP_PER_SAMPLE * (value / world) / 1e12
+    step_tflops = flop_per_sample * (value / world) / 1e12
     line = {
         "metric": "clip_mbart_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "CLIP-ViT-B/32 + mBART-50 training step (fwd+bwd+AdamW), 224x224 images, "
-                               "64-token captions", "per_gpu_batch": B, "global_batch": B * world, "seq_len": T,
+        "config": {"workload": wl_name, "per_gpu_batch": B, "global_batch": B * world, "seq_len": T,
                    "parallelism": f"dp{world}", "dropout": state.dropout, "cuda_graph": True, "ms_per_step_eager": ms_eager, "l2": "working set (>20 GB/step) exceeds the 126 MB L2",
                    "loss_last": lossv},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -251,7 +254,7 @@ def run_ours(args):
                      "peak_source": f"{peak_src} (sustained: kernel timed inside a long step)", "traffic": ncu_traffic_bytes(),
                      "kernel_ms": k_ms, "flops_per_launch": k_flops},
         "step_roofline": {"achieved": step_tflops, "peak": peak_sus, "unit": "TFLOP/s", "frac": step_tflops / peak_sus,
-                          "flop_per_sample": FLOP_PER_SAMPLE},
+                          "flop_per_sample": flop_per_sample},
         "clocks": sampler.summary() if sampler else None,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -297,6 +300,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-generate", action="store_true", help="also time beam-4 generation (configs[3])")
+    ap.add_argument("--model", default="clip-mbart", choices=["clip-mbart", "vit-bart"],
+                    help="clip-mbart = BASELINE configs[1,2] (default); vit-bart = configs[4]")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

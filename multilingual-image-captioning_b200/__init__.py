@@ -7,7 +7,7 @@ training modules need CUDA + libmic_b200.so and are imported on first attribute 
 import importlib
 
 from .configuration import (CLIPVisionConfig, MBartConfig, CLIPVisionMBartConfig, clip_mbart_config,
-                            vit_bart_config, tiny_config)
+                            vit_bart_config, tiny_config, tiny_vit_bart_config)
 from . import synthetic
 
 _LAZY = {
@@ -28,4 +28,4 @@ def __getattr__(name):
 
 
 __all__ = ["CLIPVisionConfig", "MBartConfig", "CLIPVisionMBartConfig", "clip_mbart_config", "vit_bart_config",
-           "tiny_config", "synthetic"] + list(_LAZY)
+           "tiny_config", "tiny_vit_bart_config", "synthetic"] + list(_LAZY)

@@ -137,3 +137,15 @@ def tiny_config(vocab_size: int = 1003, layers: int = 2) -> CLIPVisionMBartConfi
     t = MBartConfig(vocab_size=vocab_size, d_model=128, decoder_layers=layers, decoder_attention_heads=2,
                     decoder_ffn_dim=256, max_position_embeddings=128)
     return CLIPVisionMBartConfig(v, t)
+
+
+def tiny_vit_bart_config(vocab_size: int = 1003, layers: int = 2, image_size: int = 144) -> CLIPVisionMBartConfig:
+    """flax_vit_bart structure at test size: 16x16 patches (81+1 = 82 visual tokens > 64 exercises the general
+    attention kernels), conv bias, exact gelu, final ViT layernorm, post-LN BART decoder without final LN."""
+    v = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=layers, num_attention_heads=2,
+                         image_size=image_size, patch_size=16, hidden_act="gelu", layer_norm_eps=1e-12, patch_bias=True,
+                         pre_layernorm=False, final_layernorm=True, channel_first_input=True)
+    t = MBartConfig(vocab_size=vocab_size, d_model=128, decoder_layers=layers, decoder_attention_heads=2,
+                    decoder_ffn_dim=256, max_position_embeddings=128, scale_embedding=False, pre_layernorm=False,
+                    final_layer_norm=False, layer_norm_eps=1e-5)
+    return CLIPVisionMBartConfig(v, t, model_type="vit-bart")

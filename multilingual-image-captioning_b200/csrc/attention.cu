@@ -357,6 +357,353 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const AttnArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// General path for longer sequences (ViT-B/16: 197 tokens; BART cross-attention over 197 keys):
+//   forward : grid (B*H, ceil(Tq/64)); a CTA owns 64 queries and ALL keys (<= 256) in shared memory
+//   backward: dQ kernel  grid (B*H, query blocks)  loops over 64-key blocks (no online softmax needed: the
+//             forward saved the log-sum-exp), dK/dV kernel grid (B*H, key blocks) loops over query blocks.
+// ---------------------------------------------------------------------------------------------
+constexpr int GEN_MAX_T = 256;
+
+__device__ __forceinline__ void load_rows(const bf16* g, long long ld, int row0, int rows_valid, int nrows, bf16* s,
+                                          int tid, int nthreads) {
+  // rows [row0, row0+nrows) of a head slice -> smem rows [0, nrows); rows >= rows_valid are zero
+  for (int i = tid; i < nrows * (HD / 8); i += nthreads) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (row0 + r < rows_valid) u = *reinterpret_cast<const uint4*>(g + (long long)(row0 + r) * ld + c);
+    *reinterpret_cast<uint4*>(s + r * LDS + c) = u;
+  }
+}
+
+template <int NKB>   // number of 64-key blocks held in registers per query row block
+__global__ void __launch_bounds__(128) attention_fwd_gen_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sK = sQ + 64 * LDS;
+  bf16* sV = sK + NKB * 64 * LDS;
+  int* sMask = reinterpret_cast<int*>(sV + NKB * 64 * LDS);
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, qb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_rows(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, qb * 64, a.Tq, 64, sQ, tid, 128);
+  load_rows(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, 0, a.Tk, NKB * 64, sK, tid, 128);
+  load_rows(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, 0, a.Tk, NKB * 64, sV, tid, 128);
+  for (int j = tid; j < NKB * 64; j += 128) sMask[j] = (a.key_mask && j < a.Tk) ? a.key_mask[(long long)b * a.Tk + j] : 1;
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (qb * 64 + r0 >= a.Tq) return;
+  const int g = lane >> 2, t = lane & 3;
+  float s[NKB * 8][4];
+#pragma unroll
+  for (int nt = 0; nt < NKB * 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t af[4];
+    frag_a(sQ, r0, kk * 16, lane, af);
+#pragma unroll
+    for (int nt = 0; nt < NKB * 8; ++nt) {
+      uint32_t bfr[2];
+      frag_b(sK, nt * 8, kk * 16, lane, bfr);
+      mma_bf16_16816(s[nt], af, bfr);
+    }
+  }
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < NKB * 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = qb * 64 + r0 + g + (j >> 1) * 8, col = nt * 8 + 2 * t + (j & 1);
+      const bool ok = key_allowed(row, col, a.Tk, a.causal, a.key_mask ? sMask : nullptr);
+      s[nt][j] = ok ? s[nt][j] * a.scale : -INFINITY;
+      mx[j >> 1] = fmaxf(mx[j >> 1], s[nt][j]);
+    }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    if (mx[i] == -INFINITY) mx[i] = 0.f;
+  }
+#pragma unroll
+  for (int nt = 0; nt < NKB * 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = __expf(s[nt][j] - mx[j >> 1]);
+      s[nt][j] = p;
+      sum[j >> 1] += p;
+    }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[nd][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NKB * 4; ++kk) {
+    uint32_t af[4];
+    af[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    af[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    af[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    af[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      uint32_t bfr[2];
+      frag_b_trans(sV, kk * 16, nd * 8, lane, bfr);
+      mma_bf16_16816(o[nd], af, bfr);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = qb * 64 + r0 + g + i * 8;
+    if (row < a.Tq) {
+      const float inv = sum[i] > 0.f ? 1.0f / sum[i] : 0.f;
+      bf16* orow = a.O + ((long long)b * a.Tq + row) * a.ldo + h * HD;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        *reinterpret_cast<uint32_t*>(orow + nd * 8 + 2 * t) = pack_bf16(o[nd][2 * i] * inv, o[nd][2 * i + 1] * inv);
+      if (a.lse && t == 0) a.lse[((long long)b * a.H + h) * a.Tq + row] = mx[i] + logf(sum[i]);
+    }
+  }
+}
+
+// D[q] = sum_d dO[q][d] * O[q][d] for rows [row0, row0+nrows) -> sD[0..nrows)
+__device__ __forceinline__ void rowdot_dO_O(const AttnArgs& a, int b, int h, int row0, int nrows, float* sD, int tid,
+                                            int nthreads) {
+  const bf16* gdO = a.dO + ((long long)b * a.Tq) * a.lddo + h * HD;
+  const bf16* gO = a.O + ((long long)b * a.Tq) * a.ldo + h * HD;
+  for (int r = tid; r < nrows; r += nthreads) {
+    float d = 0.f;
+    if (row0 + r < a.Tq) {
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(gdO + (long long)(row0 + r) * a.lddo + c);
+        const uint4 w = *reinterpret_cast<const uint4*>(gO + (long long)(row0 + r) * a.ldo + c);
+        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+        const uint32_t* ww = reinterpret_cast<const uint32_t*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16(uu[j]), y = unpack_bf16(ww[j]);
+          d += x.x * y.x + x.y * y.y;
+        }
+      }
+    }
+    sD[r] = d;
+  }
+}
+
+// P and dS for a 16-query x 64-key block: s <- P (fp32), dp <- dS (fp32)
+__device__ __forceinline__ void p_ds_block(const AttnArgs& a, float (*s)[4], float (*dp)[4], int q_row0, int key0, int g,
+                                           int t, const float* lse, const float* dd, const int* sMask) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = j >> 1;
+      const int row = q_row0 + g + i * 8, col = key0 + nt * 8 + 2 * t + (j & 1);
+      const bool ok = row < a.Tq && key_allowed(row, col, a.Tk, a.causal, sMask);
+      const float p = ok ? __expf(s[nt][j] * a.scale - lse[i]) : 0.f;
+      dp[nt][j] = p * (dp[nt][j] - dd[i]) * a.scale;
+      s[nt][j] = p;
+    }
+}
+
+__global__ void __launch_bounds__(128) attention_bwd_dq_kernel(const AttnArgs a, int nkb) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sdO = sQ + 64 * LDS;
+  bf16* sK = sdO + 64 * LDS;
+  bf16* sV = sK + nkb * 64 * LDS;
+  float* sD = reinterpret_cast<float*>(sV + nkb * 64 * LDS);
+  int* sMask = reinterpret_cast<int*>(sD + 64);
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, qb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_rows(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, qb * 64, a.Tq, 64, sQ, tid, 128);
+  load_rows(a.dO + ((long long)b * a.Tq) * a.lddo + h * HD, a.lddo, qb * 64, a.Tq, 64, sdO, tid, 128);
+  load_rows(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, 0, a.Tk, nkb * 64, sK, tid, 128);
+  load_rows(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, 0, a.Tk, nkb * 64, sV, tid, 128);
+  for (int j = tid; j < nkb * 64; j += 128) sMask[j] = (a.key_mask && j < a.Tk) ? a.key_mask[(long long)b * a.Tk + j] : 1;
+  rowdot_dO_O(a, b, h, qb * 64, 64, sD, tid, 128);
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (qb * 64 + r0 >= a.Tq) return;
+  const int g = lane >> 2, t = lane & 3;
+  float lse[2], dd[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = qb * 64 + r0 + g + i * 8;
+    lse[i] = row < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + row] : 0.f;
+    dd[i] = sD[r0 + g + i * 8];
+  }
+  float dq[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[nd][j] = 0.f;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const bf16* kblk = sK + kb * 64 * LDS;
+    const bf16* vblk = sV + kb * 64 * LDS;
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[nt][j] = 0.f;
+        dp[nt][j] = 0.f;
+      }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t aq[4], ado[4];
+      frag_a(sQ, r0, kk * 16, lane, aq);
+      frag_a(sdO, r0, kk * 16, lane, ado);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t bk[2], bv[2];
+        frag_b(kblk, nt * 8, kk * 16, lane, bk);
+        frag_b(vblk, nt * 8, kk * 16, lane, bv);
+        mma_bf16_16816(s[nt], aq, bk);
+        mma_bf16_16816(dp[nt], ado, bv);
+      }
+    }
+    p_ds_block(a, s, dp, qb * 64 + r0, kb * 64, g, t, lse, dd, a.key_mask ? sMask : nullptr);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t af[4];
+      af[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+      af[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+      af[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      af[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        uint32_t bfr[2];
+        frag_b_trans(kblk, kk * 16, nd * 8, lane, bfr);
+        mma_bf16_16816(dq[nd], af, bfr);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = qb * 64 + r0 + g + i * 8;
+    if (row < a.Tq) {
+      bf16* drow = a.dQ + ((long long)b * a.Tq + row) * a.lddq + h * HD;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        *reinterpret_cast<uint32_t*>(drow + nd * 8 + 2 * t) = pack_bf16(dq[nd][2 * i], dq[nd][2 * i + 1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) attention_bwd_dkv_kernel(const AttnArgs a, int nqb) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sK = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sV = sK + 64 * LDS;
+  bf16* sP = sV + 64 * LDS;
+  bf16* sdS = sP + 64 * LDS;
+  bf16* sQ = sdS + 64 * LDS;
+  bf16* sdO = sQ + nqb * 64 * LDS;
+  float* sD = reinterpret_cast<float*>(sdO + nqb * 64 * LDS);
+  float* sLse = sD + nqb * 64;
+  int* sMask = reinterpret_cast<int*>(sLse + nqb * 64);
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, kb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_rows(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, kb * 64, a.Tk, 64, sK, tid, 128);
+  load_rows(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, kb * 64, a.Tk, 64, sV, tid, 128);
+  load_rows(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, 0, a.Tq, nqb * 64, sQ, tid, 128);
+  load_rows(a.dO + ((long long)b * a.Tq) * a.lddo + h * HD, a.lddo, 0, a.Tq, nqb * 64, sdO, tid, 128);
+  rowdot_dO_O(a, b, h, 0, nqb * 64, sD, tid, 128);
+  for (int r = tid; r < nqb * 64; r += 128) sLse[r] = r < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + r] : 0.f;
+  if (tid < 64) sMask[tid] = (a.key_mask && kb * 64 + tid < a.Tk) ? a.key_mask[(long long)b * a.Tk + kb * 64 + tid] : 1;
+  __syncthreads();
+  const int r0 = warp * 16;
+  const int g = lane >> 2, t = lane & 3;
+  float dv[8][4], dk[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dv[nd][j] = 0.f;
+      dk[nd][j] = 0.f;
+    }
+  for (int qb = 0; qb < nqb; ++qb) {
+    const bf16* qblk = sQ + qb * 64 * LDS;
+    const bf16* doblk = sdO + qb * 64 * LDS;
+    {
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[nt][j] = 0.f;
+          dp[nt][j] = 0.f;
+        }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t aq[4], ado[4];
+        frag_a(qblk, r0, kk * 16, lane, aq);
+        frag_a(doblk, r0, kk * 16, lane, ado);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          uint32_t bk[2], bv[2];
+          frag_b(sK, nt * 8, kk * 16, lane, bk);
+          frag_b(sV, nt * 8, kk * 16, lane, bv);
+          mma_bf16_16816(s[nt], aq, bk);
+          mma_bf16_16816(dp[nt], ado, bv);
+        }
+      }
+      float lse[2], dd[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        lse[i] = sLse[qb * 64 + r0 + g + i * 8];
+        dd[i] = sD[qb * 64 + r0 + g + i * 8];
+      }
+      // key index inside sMask is block-local: shift the mask pointer so that key_allowed(col) indexes col - kb*64
+      p_ds_block(a, s, dp, qb * 64 + r0, kb * 64, g, t, lse, dd, a.key_mask ? (sMask - kb * 64) : nullptr);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = r0 + g + i * 8;
+          *reinterpret_cast<uint32_t*>(sP + row * LDS + nt * 8 + 2 * t) = pack_bf16(s[nt][2 * i], s[nt][2 * i + 1]);
+          *reinterpret_cast<uint32_t*>(sdS + row * LDS + nt * 8 + 2 * t) = pack_bf16(dp[nt][2 * i], dp[nt][2 * i + 1]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      uint32_t ap[4], ads[4];
+      frag_a_trans(sP, r0, qq * 16, lane, ap);
+      frag_a_trans(sdS, r0, qq * 16, lane, ads);
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        uint32_t bdo[2], bq[2];
+        frag_b_trans(doblk, qq * 16, nd * 8, lane, bdo);
+        frag_b_trans(qblk, qq * 16, nd * 8, lane, bq);
+        mma_bf16_16816(dv[nd], ap, bdo);
+        mma_bf16_16816(dk[nd], ads, bq);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int key = kb * 64 + r0 + g + i * 8;
+    if (key < a.Tk) {
+      bf16* krow = a.dK + ((long long)b * a.Tk + key) * a.lddk + h * HD;
+      bf16* vrow = a.dV + ((long long)b * a.Tk + key) * a.lddv + h * HD;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        *reinterpret_cast<uint32_t*>(krow + nd * 8 + 2 * t) = pack_bf16(dk[nd][2 * i], dk[nd][2 * i + 1]);
+        *reinterpret_cast<uint32_t*>(vrow + nd * 8 + 2 * t) = pack_bf16(dv[nd][2 * i], dv[nd][2 * i + 1]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cached decode attention (1 query token per row), SURVEY.md A.3.
 // Self-attention reads the K/V history of a beam through an ancestor table instead of physically
 // reordering the cache (generation_clip_vision_utils.py:945-953 gathers 24 arrays every step):
@@ -482,7 +829,13 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs
 
 static int check_attn(int head_dim, int Tq, int Tk) {
   MIC_CHECK_ARG(head_dim == HD, "attention: head_dim %d != 64", head_dim);
-  MIC_CHECK_ARG(Tq >= 1 && Tq <= TMAX && Tk >= 1 && Tk <= TMAX, "attention: Tq=%d Tk=%d must be in [1,64]", Tq, Tk);
+  MIC_CHECK_ARG(Tq >= 1 && Tq <= GEN_MAX_T && Tk >= 1 && Tk <= GEN_MAX_T, "attention: Tq=%d Tk=%d must be in [1,256]", Tq,
+                Tk);
+  return MIC_OK;
+}
+template <typename K>
+static int set_smem(K kern, int bytes) {
+  MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return MIC_OK;
 }
 
@@ -497,7 +850,23 @@ extern "C" int mic_attention_fwd(void* stream, const void* Q, long long ldq, con
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
   a.O = (bf16*)O; a.ldo = ldo; a.lse = lse; a.key_mask = key_mask;
   a.causal = causal; a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.scale = scale;
-  attention_fwd_kernel<<<B * H, 128, 0, STREAM>>>(a);
+  if (Tq <= TMAX && Tk <= TMAX) {
+    attention_fwd_kernel<<<B * H, 128, 0, STREAM>>>(a);
+  } else {
+    const int nkb = (Tk + 63) / 64;
+    dim3 grid(B * H, (Tq + 63) / 64);
+    if (nkb <= 2) {
+      const int smem = (64 + 2 * 2 * 64) * LDS * 2 + 2 * 64 * 4;
+      static bool attr2 = false;
+      if (!attr2) { rc = set_smem(attention_fwd_gen_kernel<2>, smem); if (rc) return rc; attr2 = true; }
+      attention_fwd_gen_kernel<2><<<grid, 128, smem, STREAM>>>(a);
+    } else {
+      const int smem = (64 + 2 * 4 * 64) * LDS * 2 + 4 * 64 * 4;
+      static bool attr4 = false;
+      if (!attr4) { rc = set_smem(attention_fwd_gen_kernel<4>, smem); if (rc) return rc; attr4 = true; }
+      attention_fwd_gen_kernel<4><<<grid, 128, smem, STREAM>>>(a);
+    }
+  }
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
@@ -522,7 +891,19 @@ extern "C" int mic_attention_bwd(void* stream, const void* Q, long long ldq, con
   a.dO = (const bf16*)dO; a.lddo = lddo;
   a.dQ = (bf16*)dQ; a.dK = (bf16*)dK; a.dV = (bf16*)dV;
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
-  attention_bwd_kernel<<<B * H, 128, BWD_SMEM, STREAM>>>(a);
+  if (Tq <= TMAX && Tk <= TMAX) {
+    attention_bwd_kernel<<<B * H, 128, BWD_SMEM, STREAM>>>(a);
+  } else {
+    const int nkb = (Tk + 63) / 64, nqb = (Tq + 63) / 64;
+    const int smem_dq = (2 * 64 + 2 * nkb * 64) * LDS * 2 + 64 * 4 + nkb * 64 * 4;
+    const int smem_dkv = (4 * 64 + 2 * nqb * 64) * LDS * 2 + 2 * nqb * 64 * 4 + 64 * 4;
+    static int set_dq = 0, set_dkv = 0;
+    if (smem_dq > set_dq) { rc = set_smem(attention_bwd_dq_kernel, smem_dq); if (rc) return rc; set_dq = smem_dq; }
+    if (smem_dkv > set_dkv) { rc = set_smem(attention_bwd_dkv_kernel, smem_dkv); if (rc) return rc; set_dkv = smem_dkv; }
+    attention_bwd_dq_kernel<<<dim3(B * H, nqb), 128, smem_dq, STREAM>>>(a, nkb);
+    MIC_CHECK_LAUNCH();
+    attention_bwd_dkv_kernel<<<dim3(B * H, nkb), 128, smem_dkv, STREAM>>>(a, nqb);
+  }
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

@@ -112,7 +112,7 @@ class CaptionEngine:
         return dx
 
     def _dense_bwd(self, x, dy, wname, dx_out, bias=True, w_view=None, gw_view=None, gb_view=None, act=None, u=None,
-                   du=None, dropout=None):
+                   du=None, dropout=None, dgrad_residual=None):
         """Backward of y = act(x @ W + b).  x: [M,K] input, dy: [M,N] grad of the output (post-act).
         Returns dx (written into dx_out) — or None if dx_out is None."""
         ps = self.ps
@@ -137,7 +137,7 @@ class CaptionEngine:
         self._fork_side(lambda: ops.gemm(x, dyv, a_mn=True, b_mn=True, out=gw), x, dyv, gw)   # dW[K,N] = x^T dy
         if dx_out is not None:
             self._before_write(dx_out)
-            ops.gemm(dy, w, a_mn=False, b_mn=False, out=dx_out)               # dx[M,K] = dy W^T
+            ops.gemm(dy, w, a_mn=False, b_mn=False, out=dx_out, residual=dgrad_residual)   # dx[M,K] = dy W^T (+ skip grad)
         return dx_out
 
     # ------------------------------------------------------------------------------------------
@@ -196,7 +196,8 @@ class CaptionEngine:
     def decoder_forward(self, ids, key_mask, pos_ids, enc_kv, B, T, S, save=False, tag="dec", train=False):
         t, ps, b = self.t, self.ps, self.bufs
         d, M, H = t.d_model, B * T, t.decoder_attention_heads
-        assert t.pre_layernorm, "post-LN (BART) decoder: see engine_postln (config 5)"
+        if not t.pre_layernorm:
+            return self._decoder_forward_postln(ids, key_mask, pos_ids, enc_kv, B, T, S, save, tag, train)
         eps = t.layer_norm_eps
         scale = 1.0 / math.sqrt(t.head_dim)
         emb = b.get(tag + ".emb", (M, d))
@@ -239,6 +240,136 @@ class CaptionEngine:
             stL = (b.get(tag + ".lnL.mean", (M,), F32), b.get(tag + ".lnL.rstd", (M,), F32))
             x = self._ln_fwd(x, "d.ln_final", eps, b.get(tag + ".hf", (M, d)), stL)
         return x
+
+    # ------------------------------------------------------------------------------------------
+    # BART decoder (flax_vit_bart variant): POST-LN blocks  h = LN(h + dropout(sublayer(h))), no final LN
+    # (FlaxBartDecoderLayer; HF-PT twin modeling_bart.py:354-389)
+    # ------------------------------------------------------------------------------------------
+    def _decoder_forward_postln(self, ids, key_mask, pos_ids, enc_kv, B, T, S, save, tag, train):
+        t, ps, b = self.t, self.ps, self.bufs
+        d, M, H = t.d_model, B * T, t.decoder_attention_heads
+        eps = t.layer_norm_eps
+        scale = 1.0 / math.sqrt(t.head_dim)
+        drop = self._drop if train else (lambda site: None)
+        emb = b.get(tag + ".emb", (M, d))
+        st = (b.get(tag + ".emb.mean", (M,), F32), b.get(tag + ".emb.rstd", (M,), F32))
+        x = b.get(tag + ".x0", (M, d))
+        ops.embed_ln_fwd(ids, pos_ids, T, t.position_offset, ps.w("shared"), ps.w("d.pos"), self.emb_scale,
+                         ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), eps, emb, x, st[0], st[1], dropout=drop(1))
+        for l in range(t.decoder_layers):
+            n = f"d.{l}"
+            sfx = f".{l}" if save else ""
+
+            def stats(nm):
+                return (b.get(tag + nm + ".mean" + sfx, (M,), F32), b.get(tag + nm + ".rstd" + sfx, (M,), F32))
+            qkv = ops.gemm(x, ps.w(n + ".sa_qkv.w"), b_mn=True, bias=ps.f(n + ".sa_qkv.b"),
+                           out=b.get(tag + ".qkv" + sfx, (M, 3 * d)))
+            sa = b.get(tag + ".sa" + sfx, (M, d))
+            ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, b.get(tag + ".lse1" + sfx, (B, H, T), F32),
+                              key_mask, True, B, H, T, T, scale)
+            y1 = ops.gemm(sa, ps.w(n + ".sa_o.w"), b_mn=True, bias=ps.f(n + ".sa_o.b"), residual=x,
+                          out=b.get(tag + ".y1" + sfx, (M, d)), dropout=drop(10 + 4 * l))
+            x1 = self._ln_fwd(y1, n + ".ln_sa", eps, b.get(tag + ".x1" + sfx, (M, d)), stats(".lnA"))
+            qc = ops.gemm(x1, ps.w(n + ".ca_q.w"), b_mn=True, bias=ps.f(n + ".ca_q.b"), out=b.get(tag + ".qc" + sfx, (M, d)))
+            ca = b.get(tag + ".ca" + sfx, (M, d))
+            kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
+            vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+            ops.attention_fwd(qc, kl, vl, ca, b.get(tag + ".lse2" + sfx, (B, H, T), F32), None, False, B, H, T, S, scale)
+            y2 = ops.gemm(ca, ps.w(n + ".ca_o.w"), b_mn=True, bias=ps.f(n + ".ca_o.b"), residual=x1,
+                          out=b.get(tag + ".y2" + sfx, (M, d)), dropout=drop(11 + 4 * l))
+            x2 = self._ln_fwd(y2, n + ".ln_ca", eps, b.get(tag + ".x2" + sfx, (M, d)), stats(".lnC"))
+            u = b.get(tag + ".u" + sfx, (M, t.decoder_ffn_dim)) if save else None
+            g = ops.gemm(x2, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=t.activation_function,
+                         pre_act_out=u, out=b.get(tag + ".g" + sfx, (M, t.decoder_ffn_dim)))
+            y3 = ops.gemm(g, ps.w(n + ".fc2.w"), b_mn=True, bias=ps.f(n + ".fc2.b"), residual=x2,
+                          out=b.get(tag + ".y3" + sfx, (M, d)), dropout=drop(12 + 4 * l))
+            x = self._ln_fwd(y3, n + ".ln_f", eps, b.get(tag + f".x{l + 1}" if save else tag + f".xping{l & 1}", (M, d)),
+                             stats(".lnF"))
+        if t.final_layer_norm:
+            stL = (b.get(tag + ".lnL.mean", (M,), F32), b.get(tag + ".lnL.rstd", (M,), F32))
+            x = self._ln_fwd(x, "d.ln_final", eps, b.get(tag + ".hf", (M, d)), stL)
+        return x
+
+    def _decoder_backward_preln(self, dx, km, enc_kv, d_enc_kv, B, T, S, tg):
+        t, b = self.t, self.bufs
+        d, M = t.d_model, B * T
+        H = t.decoder_attention_heads
+        scale = 1.0 / math.sqrt(t.head_dim)
+        dg = b.get("tr.dg", (M, t.decoder_ffn_dim))
+        du = b.get("tr.du", (M, t.decoder_ffn_dim))
+        dtmp = b.get("tr.dtmp", (M, d))
+        dqkv = b.get("tr.dqkv", (M, 3 * d))
+        dqc = b.get("tr.dqc", (M, d))
+        for l in reversed(range(t.decoder_layers)):
+            n = f"d.{l}"
+            sfx = f".{l}"
+            g_, u_, lnF = b.t[tg + ".g" + sfx], b.t[tg + ".u" + sfx], b.t[tg + ".lnF" + sfx]
+            x2, x1, x0 = b.t[tg + ".x2" + sfx], b.t[tg + ".x1" + sfx], b.t[tg + f".x{l}"]
+            # FFN
+            self._dense_bwd(g_, dx, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
+            self._dense_bwd(lnF, dg, n + ".fc1", dtmp, act=t.activation_function, u=u_, du=du)
+            self._ln_bwd(dtmp, x2, n + ".ln_f", (b.t[tg + ".lnF.mean" + sfx], b.t[tg + ".lnF.rstd" + sfx]), dx, dx)
+            # cross attention
+            ca, qc, lnC = b.t[tg + ".ca" + sfx], b.t[tg + ".qc" + sfx], b.t[tg + ".lnC" + sfx]
+            self._dense_bwd(ca, dx, n + ".ca_o", dtmp, dropout=self._drop(11 + 4 * l))
+            kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
+            vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+            self._before_write(dqc, d_enc_kv)
+            ops.attention_bwd(qc, kl, vl, ca, dtmp, b.t[tg + ".lse2" + sfx], None, False, dqc,
+                              d_enc_kv[:, l * 2 * d: l * 2 * d + d], d_enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d],
+                              B, H, T, S, scale)
+            self._dense_bwd(lnC, dqc, n + ".ca_q", dtmp)
+            self._ln_bwd(dtmp, x1, n + ".ln_ca", (b.t[tg + ".lnC.mean" + sfx], b.t[tg + ".lnC.rstd" + sfx]), dx, dx)
+            # self attention
+            sa, qkv, lnA = b.t[tg + ".sa" + sfx], b.t[tg + ".qkv" + sfx], b.t[tg + ".lnA" + sfx]
+            self._dense_bwd(sa, dx, n + ".sa_o", dtmp, dropout=self._drop(10 + 4 * l))
+            self._before_write(dqkv)
+            ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, dtmp, b.t[tg + ".lse1" + sfx], km, True,
+                              dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, T, T, scale)
+            self._dense_bwd(lnA, dqkv, n + ".sa_qkv", dtmp)
+            self._ln_bwd(dtmp, x0, n + ".ln_sa", (b.t[tg + ".lnA.mean" + sfx], b.t[tg + ".lnA.rstd" + sfx]), dx, dx)
+    def _decoder_backward_postln(self, dx, km, enc_kv, d_enc_kv, B, T, S, tg):
+        """dx: gradient w.r.t. the last layer's output (in place buffer).  Returns the gradient w.r.t. x0."""
+        t, b = self.t, self.bufs
+        d, M, H = t.d_model, B * T, t.decoder_attention_heads
+        scale = 1.0 / math.sqrt(t.head_dim)
+        dg = b.get("tr.dg", (M, t.decoder_ffn_dim))
+        du = b.get("tr.du", (M, t.decoder_ffn_dim))
+        dy = b.get("tr.dy", (M, d))
+        dtmp = b.get("tr.dtmp", (M, d))
+        dqkv = b.get("tr.dqkv", (M, 3 * d))
+        dqc = b.get("tr.dqc", (M, d))
+        for l in reversed(range(t.decoder_layers)):
+            n = f"d.{l}"
+            sfx = f".{l}"
+
+            def st(nm):
+                return (b.t[tg + nm + ".mean" + sfx], b.t[tg + nm + ".rstd" + sfx])
+            # FFN block: x3 = LN(y3), y3 = x2 + drop(fc2(gelu(fc1(x2))))
+            self._ln_bwd(dx, b.t[tg + ".y3" + sfx], n + ".ln_f", st(".lnF"), None, dy)
+            self._dense_bwd(b.t[tg + ".g" + sfx], dy, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
+            self._dense_bwd(b.t[tg + ".x2" + sfx], dg, n + ".fc1", dx, act=t.activation_function, u=b.t[tg + ".u" + sfx],
+                            du=du, dgrad_residual=dy)                                  # dx2 = dy3 + fc1 dgrad
+            # cross-attention block
+            self._ln_bwd(dx, b.t[tg + ".y2" + sfx], n + ".ln_ca", st(".lnC"), None, dy)
+            self._dense_bwd(b.t[tg + ".ca" + sfx], dy, n + ".ca_o", dtmp, dropout=self._drop(11 + 4 * l))
+            kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
+            vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
+            self._before_write(dqc, d_enc_kv)
+            ops.attention_bwd(b.t[tg + ".qc" + sfx], kl, vl, b.t[tg + ".ca" + sfx], dtmp, b.t[tg + ".lse2" + sfx], None,
+                              False, dqc, d_enc_kv[:, l * 2 * d: l * 2 * d + d],
+                              d_enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d], B, H, T, S, scale)
+            self._dense_bwd(b.t[tg + ".x1" + sfx], dqc, n + ".ca_q", dx, dgrad_residual=dy)   # dx1 = dy2 + q dgrad
+            # self-attention block
+            self._ln_bwd(dx, b.t[tg + ".y1" + sfx], n + ".ln_sa", st(".lnA"), None, dy)
+            self._dense_bwd(b.t[tg + ".sa" + sfx], dy, n + ".sa_o", dtmp, dropout=self._drop(10 + 4 * l))
+            qkv = b.t[tg + ".qkv" + sfx]
+            self._before_write(dqkv)
+            ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], b.t[tg + ".sa" + sfx], dtmp,
+                              b.t[tg + ".lse1" + sfx], km, True, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H,
+                              T, T, scale)
+            self._dense_bwd(b.t[tg + f".x{l}"], dqkv, n + ".sa_qkv", dx, dgrad_residual=dy)   # dx0 = dy1 + qkv dgrad
+        return dx
 
     # ------------------------------------------------------------------------------------------
     # loss (fused lm_head + CE) and logits
@@ -309,43 +440,15 @@ class CaptionEngine:
                          (b.t[tg + ".lnL.mean"], b.t[tg + ".lnL.rstd"]), None, dx)
         else:
             dx.copy_(dhf)
+            ps.g("d.ln_final.scale").zero_()     # BART has no final LayerNorm: parameters exist in the tree, unused
+            ps.g("d.ln_final.bias").zero_()
         # ---------------- backward: decoder layers ----------------
-        H = t.decoder_attention_heads
-        scale = 1.0 / math.sqrt(t.head_dim)
-        dg = b.get("tr.dg", (M, t.decoder_ffn_dim))
-        du = b.get("tr.du", (M, t.decoder_ffn_dim))
-        dtmp = b.get("tr.dtmp", (M, d))
-        dqkv = b.get("tr.dqkv", (M, 3 * d))
-        dqc = b.get("tr.dqc", (M, d))
         d_enc_kv = b.get("tr.d_enc_kv", (Mv, t.decoder_layers * 2 * d))
-        for l in reversed(range(t.decoder_layers)):
-            n = f"d.{l}"
-            sfx = f".{l}"
-            g_, u_, lnF = b.t[tg + ".g" + sfx], b.t[tg + ".u" + sfx], b.t[tg + ".lnF" + sfx]
-            x2, x1, x0 = b.t[tg + ".x2" + sfx], b.t[tg + ".x1" + sfx], b.t[tg + f".x{l}"]
-            # FFN
-            self._dense_bwd(g_, dx, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
-            self._dense_bwd(lnF, dg, n + ".fc1", dtmp, act=t.activation_function, u=u_, du=du)
-            self._ln_bwd(dtmp, x2, n + ".ln_f", (b.t[tg + ".lnF.mean" + sfx], b.t[tg + ".lnF.rstd" + sfx]), dx, dx)
-            # cross attention
-            ca, qc, lnC = b.t[tg + ".ca" + sfx], b.t[tg + ".qc" + sfx], b.t[tg + ".lnC" + sfx]
-            self._dense_bwd(ca, dx, n + ".ca_o", dtmp, dropout=self._drop(11 + 4 * l))
-            kl = enc_kv[:, l * 2 * d: l * 2 * d + d]
-            vl = enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
-            self._before_write(dqc, d_enc_kv)
-            ops.attention_bwd(qc, kl, vl, ca, dtmp, b.t[tg + ".lse2" + sfx], None, False, dqc,
-                              d_enc_kv[:, l * 2 * d: l * 2 * d + d], d_enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d],
-                              B, H, T, S, scale)
-            self._dense_bwd(lnC, dqc, n + ".ca_q", dtmp)
-            self._ln_bwd(dtmp, x1, n + ".ln_ca", (b.t[tg + ".lnC.mean" + sfx], b.t[tg + ".lnC.rstd" + sfx]), dx, dx)
-            # self attention
-            sa, qkv, lnA = b.t[tg + ".sa" + sfx], b.t[tg + ".qkv" + sfx], b.t[tg + ".lnA" + sfx]
-            self._dense_bwd(sa, dx, n + ".sa_o", dtmp, dropout=self._drop(10 + 4 * l))
-            self._before_write(dqkv)
-            ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], sa, dtmp, b.t[tg + ".lse1" + sfx], km, True,
-                              dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, T, T, scale)
-            self._dense_bwd(lnA, dqkv, n + ".sa_qkv", dtmp)
-            self._ln_bwd(dtmp, x0, n + ".ln_sa", (b.t[tg + ".lnA.mean" + sfx], b.t[tg + ".lnA.rstd" + sfx]), dx, dx)
+        dtmp = b.get("tr.dtmp", (M, d))
+        if not t.pre_layernorm:
+            dx = self._decoder_backward_postln(dx, km, enc_kv, d_enc_kv, B, T, S, tg)
+        else:
+            self._decoder_backward_preln(dx, km, enc_kv, d_enc_kv, B, T, S, tg)
         # embedding
         if self._drop(1) is not None:       # dropout after layernorm_embedding
             dmask = b.get("tr.dmask", (M, d))

@@ -217,3 +217,39 @@ def test_train_step_with_dropout_runs_and_differs_per_step():
     state0 = mic_b200.TrainState(model, lambda step: 0.0, dropout=0.0)
     _, m0 = mic_b200.train_step(state0, batch)
     assert abs(float(m0["loss"]) - det) < 2e-3
+
+
+def test_vit_bart_variant_forward_and_gradients_match_oracle():
+    """flax_vit_bart (BASELINE configs[4]): channel-first pixels, 16x16 patches with conv bias,
+    exact-gelu ViT with final layernorm, POST-LN BART decoder without final LN; 82 visual tokens."""
+    cfg = mic_b200.tiny_vit_bart_config(vocab_size=1003, layers=2)
+    assert cfg.clip_vision_config.num_tokens == 82 and not cfg.mbart_config.pre_layernorm
+    params = synthetic.make_params(cfg, seed=2, perturbed=True, std=0.05)
+    batch = synthetic.make_batch(cfg, 3, seq_len=16, seed=1, min_len=4)
+    assert batch["pixel_values"].shape == (3, 3, 144, 144)
+    model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg)
+    model.params = params
+    logits = model(batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"]).logits.float().cpu()
+    p = rm.to_torch_tree(params)
+    with torch.no_grad():
+        ref = rm.forward_logits(p, batch["pixel_values"], batch["decoder_input_ids"], batch["attention_mask"], None, cfg)
+    rel = float((logits - ref).abs().max() / ref.abs().max())
+    assert rel < 3e-2, rel
+    model.store.ensure_grad()
+    model.store.grad.fill_(float("nan"))
+    ws = model.engine.forward_backward(torch.from_numpy(batch["pixel_values"]), torch.from_numpy(batch["decoder_input_ids"]),
+                                       torch.from_numpy(batch["attention_mask"]), torch.from_numpy(batch["input_ids"]), 0.1)
+    torch.cuda.synchronize()
+    loss_ref, grads_ref, _ = rm.loss_and_grads(params, batch, cfg, 0.1)
+    assert abs(float(ws["out"][0]) - loss_ref) < 2e-2
+    got = dict(_flat(model.store.to_numpy_tree(model.store.grad)))
+    want = dict(_flat(grads_ref))
+    bad = []
+    for k in sorted(want):
+        g, w = got[k], want[k]
+        assert np.isfinite(g).all(), f"non-finite / unwritten gradient: {k}"
+        denom = np.linalg.norm(w)
+        err = np.linalg.norm(g - w) / denom if denom > 1e-6 else np.abs(g).max()
+        if err > 0.08:
+            bad.append((round(float(err), 4), k))
+    assert not bad, bad[:10]

@@ -265,7 +265,9 @@ def _ref_attn(q, k, v, key_mask, causal, scale):
 
 
 @pytest.mark.parametrize("Tq,Tk,causal,masked", [(64, 64, True, True), (50, 50, False, False), (64, 50, False, False),
-                                                 (5, 5, False, False), (16, 16, True, True), (33, 7, False, False)])
+                                                 (5, 5, False, False), (16, 16, True, True), (33, 7, False, False),
+                                                 (197, 197, False, False), (64, 197, False, False),
+                                                 (130, 100, True, True), (82, 82, False, True), (16, 82, False, False)])
 def test_attention_fwd_bwd(Tq, Tk, causal, masked):
     B, H, hd = 3, 2, 64
     d = H * hd
