@@ -193,13 +193,16 @@ def _greedy_search(p, enc, config, g, return_trace=False):
     return out
 
 
-def _beam_search(p, enc, config, g, return_trace=False):
+def _beam_search(p, enc, config, g, return_trace=False, logits_fn=None, batch_size=None):
     """`_beam_search` (:665-990), statement by statement; arrays are (batch, beams, ...)."""
-    B = enc.shape[0]
+    # logits_fn(cur_len, running_sequences[B*K, L]) -> logits (B*K, V): test hook that replaces the decoder so
+    # the bookkeeping can be compared bit-for-bit with the CUDA kernels on identical log-probs
+    B = enc.shape[0] if logits_fn is None else batch_size
     K, L, pad, eos = g["num_beams"], g["max_length"], g["pad_token_id"], g["eos_token_id"]
     lp, early = g["length_penalty"], bool(g["early_stopping"])
     V = config.mbart_config.vocab_size
-    enc_rows = enc[:, None].expand(B, K, *enc.shape[1:]).reshape(B * K, *enc.shape[1:])   # :299-307, flatten
+    enc_rows = None if logits_fn is not None else \
+        enc[:, None].expand(B, K, *enc.shape[1:]).reshape(B * K, *enc.shape[1:])          # :299-307, flatten
     sequences = np.full((B, K, L), pad, dtype=np.int32)
     running_sequences = np.full((B, K, L), pad, dtype=np.int32)
     running_sequences[:, :, 0] = g["decoder_start_token_id"]
@@ -224,7 +227,10 @@ def _beam_search(p, enc, config, g, return_trace=False):
     while first or cond():
         first = False
         token = running_sequences[:, :, cur_len - 1].reshape(B * K)                  # :830-836
-        logits = decode_step(p, token, pos, enc_rows, cache, config)                  # (B*K, V)
+        if logits_fn is not None:
+            logits = logits_fn(cur_len, running_sequences.reshape(B * K, L))
+        else:
+            logits = decode_step(p, token, pos, enc_rows, cache, config)              # (B*K, V)
         log_probs = log_softmax(logits)                                               # :850
         log_probs = apply_processors(log_probs, cur_len, min_length=g["min_length"], eos_token_id=eos,
                                      forced_bos_token_id=g["forced_bos_token_id"],
@@ -232,6 +238,7 @@ def _beam_search(p, enc, config, g, return_trace=False):
         log_probs = log_probs.reshape(B, K, V) + running_scores[:, :, None]           # :857
         flat = log_probs.reshape(B, K * V).astype(np.float32)
         topk_log_probs, topk_indices = top_k(flat, 2 * K)                             # :873
+        topk_raw = topk_log_probs.copy()
         topk_beam = topk_indices // V
         topk_running = running_sequences[bidx, topk_beam]                             # (B, 2K, L)
         topk_ids = (topk_indices % V).astype(np.int32)
@@ -244,7 +251,8 @@ def _beam_search(p, enc, config, g, return_trace=False):
         next_running_scores = topk_log_probs[bidx, next_topk_indices]
         if return_trace:
             rest = np.sort(flat, axis=-1)[:, -(2 * K + 1)]
-            trace.append({"cur_len": cur_len, "topk_log_probs": topk_log_probs.copy(),
+            trace.append({"cur_len": cur_len, "topk_log_probs": topk_log_probs.copy(), "topk_raw": topk_raw,
+                          "did_finish": did_finish.copy(),
                           "topk_indices": topk_indices.copy(), "ninth": rest.copy()})
         # :910-919 (re-uses the penalised topk_log_probs)
         topk_log_probs = (topk_log_probs / np.float32(float(cur_len) ** lp)).astype(np.float32)
@@ -273,5 +281,7 @@ def _beam_search(p, enc, config, g, return_trace=False):
     if return_trace:
         out["trace"] = trace
         out["all_sequences"] = out_seq
+        out["state"] = {"running_seq": running_sequences, "running_scores": running_scores, "sequences": sequences,
+                        "scores": scores, "finished": is_sent_finished.astype(np.int32), "cur_len": cur_len}
     _ = initial_running_flat  # processors ignore input_ids; kept to document the :852 closure quirk
     return out
