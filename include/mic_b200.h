@@ -28,6 +28,15 @@ extern "C" {
 const char* mic_last_error(void);
 int mic_abi_version(void);
 
+/* Launch behaviour of every entry point called afterwards on this thread (-1 = leave unchanged).
+ * programmatic_dependent_launch (default 0): kernels are launched with
+ *   cudaLaunchAttributeProgrammaticStreamSerialization and call griddepcontrol.wait before touching any buffer,
+ *   so their prologue (barrier init, TMEM alloc, descriptor prefetch) overlaps the previous kernel's tail.
+ * gemm_b_static (default 0): the caller promises that the B operand (the weight) of the following
+ *   mic_gemm_bf16 / mic_lm_head_search calls is not written by any kernel still in flight (decode loop:
+ *   frozen parameters), so the first pipeline stages are filled with weight tiles BEFORE that wait. */
+int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static);
+
 /* ---- dense contraction ------------------------------------------------------------------------
  * D[M,N] = act(A[M,K] * B[N,K]^T + bias) + residual        (tcgen05/TMEM, TMA-fed, bf16 in, fp32 acc)
  * a_mn_major / b_mn_major = 0: operand stored [rows, K] (K contiguous); 1: stored [K, rows].

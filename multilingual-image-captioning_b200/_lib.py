@@ -18,6 +18,7 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argument ctypes (return type is always int unless listed in _RET)
 SIGNATURES = {
     "mic_abi_version": [],
+    "mic_launch_options": [I, I],
     "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I, P, I, F],
     "mic_lm_head_num_partials": [I],
     "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P, P, L],

@@ -727,6 +727,8 @@ struct DecAttnArgs {
 };
 
 __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_p[4][128];
   __shared__ int s_row[4][128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -919,7 +921,6 @@ extern "C" int mic_decode_attention(void* stream, const void* q, long long ldq, 
   a.q = (const bf16*)q; a.ldq = ldq; a.kc = (const bf16*)k_cache; a.vc = (const bf16*)v_cache; a.ldkv = ldkv;
   a.anc = ancestors; a.T = cache_len; a.n_keys = n_keys; a.rows_per_kv = rows_per_kv < 1 ? 1 : rows_per_kv;
   a.o = (bf16*)o; a.ldo = ldo; a.R = R; a.H = H; a.scale = scale;
-  decode_attention_kernel<<<(R * H + 3) / 4, 128, 0, STREAM>>>(a);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(decode_attention_kernel, dim3((R * H + 3) / 4), dim3(128), 0, STREAM, a));
   return MIC_OK;
 }

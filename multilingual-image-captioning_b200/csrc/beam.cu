@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(128)
 search_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, const float* __restrict__ cval,
                     const int* __restrict__ cidx, int nparts, int R, float* __restrict__ row_lp,
                     int* __restrict__ row_tok, float* __restrict__ row_max_lse) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -122,6 +124,8 @@ struct BeamArgs {
 };
 
 __global__ void __launch_bounds__(32) beam_step_kernel(const BeamArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ int sh[];
   if (*a.active == 0) return;
   const int b = blockIdx.x, lane = threadIdx.x;
@@ -257,6 +261,8 @@ __global__ void __launch_bounds__(256)
 beam_cond_kernel(const float* __restrict__ running_scores, const float* __restrict__ scores,
                  const int* __restrict__ finished, int B, int K, int cur_len, int max_length, float length_penalty,
                  int early_stopping, int* __restrict__ active) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_improve, s_allfin;
   if (threadIdx.x == 0) {
     s_improve = 1;
@@ -288,6 +294,8 @@ __global__ void beam_finalize_kernel(const int* __restrict__ sequences, const fl
                                      const int* __restrict__ finished, const int* __restrict__ running_seq,
                                      const float* __restrict__ running_scores, int B, int K, int L,
                                      int* __restrict__ out_seq, float* __restrict__ out_scores) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   int any = 0;
   for (int k = 0; k < K; ++k) any |= finished[b * K + k];
@@ -302,6 +310,8 @@ __global__ void beam_finalize_kernel(const int* __restrict__ sequences, const fl
 __global__ void greedy_step_kernel(const int* __restrict__ row_tok, int forced_token, int R, int L, int cur_len,
                                    int eos, int pad, int* __restrict__ sequences, int* __restrict__ finished,
                                    int* __restrict__ next_token, int* __restrict__ active) {
+  pdl_trigger();
+  pdl_wait();
   if (*active == 0) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
@@ -315,6 +325,8 @@ __global__ void greedy_step_kernel(const int* __restrict__ row_tok, int forced_t
 
 __global__ void greedy_cond_kernel(const int* __restrict__ finished, int R, int cur_len, int max_length,
                                    int* __restrict__ active) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_all;
   if (threadIdx.x == 0) s_all = 1;
   __syncthreads();
@@ -332,9 +344,8 @@ __global__ void greedy_cond_kernel(const int* __restrict__ finished, int R, int 
 extern "C" int mic_search_merge(void* stream, const float* pmax, const float* psum, const float* cand_val,
                                 const int* cand_idx, int num_partials, int R, float* row_lp, int* row_tok,
                                 float* row_max_logsum) {
-  search_merge_kernel<<<(R + 3) / 4, 128, 0, STREAM>>>(pmax, psum, cand_val, cand_idx, num_partials, R, row_lp,
-                                                       row_tok, row_max_logsum);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(search_merge_kernel, dim3((R + 3) / 4), dim3(128), 0, STREAM, pmax, psum, cand_val, cand_idx, num_partials, R, row_lp,
+                                                       row_tok, row_max_logsum));
   return MIC_OK;
 }
 
@@ -352,39 +363,34 @@ extern "C" int mic_beam_step(void* stream, const float* row_lp, const int* row_t
   a.finished = finished; a.ancestors = ancestors; a.next_token = next_token; a.active = active; a.all_flags = nullptr;
   const size_t smem = (size_t)3 * K * L * sizeof(int);
   MIC_CHECK_ARG(smem <= 40 * 1024, "beam_step: max_length %d too large", L);
-  beam_step_kernel<<<B, 32, smem, STREAM>>>(a);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(beam_step_kernel, dim3(B), dim3(32), smem, STREAM, a));
   return MIC_OK;
 }
 
 extern "C" int mic_beam_cond(void* stream, const float* running_scores, const float* scores, const int* finished,
                              int B, int K, int cur_len, int max_length, float length_penalty, int early_stopping,
                              int* active) {
-  beam_cond_kernel<<<1, 256, 0, STREAM>>>(running_scores, scores, finished, B, K, cur_len, max_length, length_penalty,
-                                          early_stopping, active);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(beam_cond_kernel, dim3(1), dim3(256), 0, STREAM, running_scores, scores, finished, B, K, cur_len, max_length, length_penalty,
+                                          early_stopping, active));
   return MIC_OK;
 }
 
 extern "C" int mic_beam_finalize(void* stream, const int* sequences, const float* scores, const int* finished,
                                  const int* running_seq, const float* running_scores, int B, int K, int L,
                                  int* out_seq, float* out_scores) {
-  beam_finalize_kernel<<<B, 64, 0, STREAM>>>(sequences, scores, finished, running_seq, running_scores, B, K, L,
-                                             out_seq, out_scores);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(beam_finalize_kernel, dim3(B), dim3(64), 0, STREAM, sequences, scores, finished, running_seq, running_scores, B, K, L,
+                                             out_seq, out_scores));
   return MIC_OK;
 }
 
 extern "C" int mic_greedy_step(void* stream, const int* row_tok, int forced_token, int R, int L, int cur_len, int eos,
                                int pad, int* sequences, int* finished, int* next_token, int* active) {
-  greedy_step_kernel<<<(R + 127) / 128, 128, 0, STREAM>>>(row_tok, forced_token, R, L, cur_len, eos, pad, sequences,
-                                                          finished, next_token, active);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(greedy_step_kernel, dim3((R + 127) / 128), dim3(128), 0, STREAM, row_tok, forced_token, R, L, cur_len, eos, pad, sequences,
+                                                          finished, next_token, active));
   return MIC_OK;
 }
 
 extern "C" int mic_greedy_cond(void* stream, const int* finished, int R, int cur_len, int max_length, int* active) {
-  greedy_cond_kernel<<<1, 256, 0, STREAM>>>(finished, R, cur_len, max_length, active);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(greedy_cond_kernel, dim3(1), dim3(256), 0, STREAM, finished, R, cur_len, max_length, active));
   return MIC_OK;
 }

@@ -34,6 +34,38 @@ void mic_set_error(const char* fmt, ...);
 #define MIC_CHECK_LAUNCH() MIC_CHECK_CUDA(cudaGetLastError())
 
 // ------------------------------------------------------------------------------------------------
+// launch plumbing: every kernel goes through mic_launch so that programmatic dependent launch (PDL) can be
+// switched on for all of them.  A kernel launched with the attribute may start while its predecessor in the
+// stream is still running; it must execute pdl_wait() before it reads or writes anything a predecessor
+// touches (everything before that point - barrier init, TMEM alloc, descriptor prefetch, loads of operands
+// the caller declared static - overlaps the predecessor's tail).  pdl_trigger() lets the successor start.
+// ------------------------------------------------------------------------------------------------
+struct MicLaunchOptions {
+  int pdl;        // launch with cudaLaunchAttributeProgrammaticStreamSerialization
+  int static_b;   // GEMM B operands (weights) are not written by any kernel in flight: prefetch before pdl_wait
+};
+extern thread_local MicLaunchOptions g_mic_launch;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t mic_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_mic_launch.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
                                                             const float* __restrict__ beta, float eps,
                                                             bf16* __restrict__ y, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, int M, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(256)
 residual_ln_fwd_kernel(float* __restrict__ acc, const float* __restrict__ bias, bf16* __restrict__ x,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                        bf16* __restrict__ y, int M, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -400,6 +404,8 @@ embed_ln_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, bf16* __restrict__ emb,
                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int d,
                     DropoutParams drop) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -753,16 +759,14 @@ inline int grid_for(long long work_items, int per_block, int cap_mult = 8) {
 extern "C" int mic_layernorm_fwd(void* stream, const void* x, const float* gamma, const float* beta, float eps,
                                  void* y, float* mean, float* rstd, int M, int d) {
   MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm: d=%d must be a multiple of 8 and <= 1024", d);
-  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, M, d);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(layernorm_fwd_kernel, dim3((M + 7) / 8), dim3(256), 0, STREAM, (const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, M, d));
   return MIC_OK;
 }
 
 extern "C" int mic_residual_ln_fwd(void* stream, float* acc, const float* bias, void* x, const float* gamma,
                                    const float* beta, float eps, void* y, int M, int d) {
   MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "residual_ln: d=%d must be a multiple of 8 and <= 1024", d);
-  residual_ln_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(acc, bias, (bf16*)x, gamma, beta, eps, (bf16*)y, M, d);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(residual_ln_fwd_kernel, dim3((M + 7) / 8), dim3(256), 0, STREAM, acc, bias, (bf16*)x, gamma, beta, eps, (bf16*)y, M, d));
   return MIC_OK;
 }
 
@@ -852,10 +856,9 @@ extern "C" int mic_embed_ln_fwd(void* stream, const int* ids, const int* pos_ids
   drop.site = drop_site;
   drop.thr16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
   drop.scale = 65536.0f / (65536.0f - (float)drop.thr16);
-  embed_ln_fwd_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>(ids, pos_ids, pos_mod, pos_offset, (const bf16*)table,
+  MIC_CHECK_CUDA(mic_launch(embed_ln_fwd_kernel, dim3((M + 7) / 8), dim3(256), 0, STREAM, ids, pos_ids, pos_mod, pos_offset, (const bf16*)table,
                                                        (const bf16*)pos_table, scale, gamma, beta, eps, (bf16*)emb,
-                                                       (bf16*)y, mean, rstd, M, d, drop);
-  MIC_CHECK_LAUNCH();
+                                                       (bf16*)y, mean, rstd, M, d, drop));
   return MIC_OK;
 }
 

@@ -20,6 +20,13 @@ void mic_set_error(const char* fmt, ...) {
 extern "C" const char* mic_last_error(void) { return g_err; }
 extern "C" int mic_abi_version(void) { return MIC_B200_ABI_VERSION; }
 
+thread_local MicLaunchOptions g_mic_launch = {0, 0};   // measured on B200: PDL does not pay inside CUDA graphs (tools/microbench_pdl.py)
+extern "C" int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static) {
+  if (programmatic_dependent_launch >= 0) g_mic_launch.pdl = programmatic_dependent_launch != 0;
+  if (gemm_b_static >= 0) g_mic_launch.static_b = gemm_b_static != 0;
+  return MIC_OK;
+}
+
 int mic_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -132,6 +139,7 @@ static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long l
   if (s.group_m < 1) s.group_m = 1;
   s.split_k = 1;
   s.kb_per_split = (K + BLOCK_K - 1) / BLOCK_K;
+  s.prefetch_b = 0;
   return MIC_OK;
 }
 
@@ -145,8 +153,8 @@ static int launch_one(cudaStream_t stream, const Operands& o, const typename Epi
   }
   const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks * o.shape.split_k;
   const int grid = tiles < mic_num_sms() ? tiles : mic_num_sms();
-  kern<<<grid, Cfg<BN, Epi::NBUF, Epi::EW>::THREADS, Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.td, o.td2, o.shape, ep);
-  MIC_CHECK_LAUNCH();
+  MIC_CHECK_CUDA(mic_launch(kern, dim3(grid), dim3(Cfg<BN, Epi::NBUF, Epi::EW>::THREADS),
+                            Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES, stream, o.ta, o.tb, o.td, o.td2, o.shape, ep));
   return MIC_OK;
 }
 
@@ -225,6 +233,7 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
       }
     }
   }
+  o.shape.prefetch_b = g_mic_launch.static_b;
   if (split_k > 1) {
     MIC_CHECK_ARG(can_split, "split_k needs a plain fp32 TMA-storable output (no bias/act/residual)");
     o.shape.kb_per_split = (nkb + split_k - 1) / split_k;
@@ -302,8 +311,8 @@ extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, co
     MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      o.ta, o.tb, o.td, o.td2, o.shape, ep);
-  MIC_CHECK_LAUNCH();
+  o.shape.prefetch_b = g_mic_launch.static_b;
+  MIC_CHECK_CUDA(mic_launch(kern, dim3(search_grid(M)), dim3(NUM_THREADS), Cfg<256>::SMEM_BYTES,
+                            reinterpret_cast<cudaStream_t>(stream), o.ta, o.tb, o.td, o.td2, o.shape, ep));
   return MIC_OK;
 }

@@ -170,16 +170,26 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
 
 
 @torch.no_grad()
-def generate(engine, pixel_values, *, use_cuda_graph=True, **kw):
+def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_weights=None, **kw):
     """`generate` :128-336.  encode() truncates pixels to int32 first (modeling_clip_vision_mbart.py:330).
     The first call for a given (batch, search settings) runs eagerly (allocates every buffer); the whole
     loop is then captured into ONE CUDA graph and later calls only copy the pixels in and replay it."""
     if kw["num_beams"] > 4:
         raise NotImplementedError("beam-step kernel keeps 2*num_beams <= 8 candidates (num_beams <= 4)")
     px = pixel_values.to(engine.dev, F32).contiguous()
+    # parameters are frozen while the loop runs: GEMMs prefetch weight tiles ahead of their dependency wait
+    prefetch_weights = pdl if prefetch_weights is None else prefetch_weights
+    ops.launch_options(pdl=int(pdl), gemm_b_static=int(prefetch_weights))
+    try:
+        return _generate(engine, px, use_cuda_graph, (pdl, prefetch_weights), kw)
+    finally:
+        ops.launch_options(pdl=0, gemm_b_static=0)
+
+
+def _generate(engine, px, use_cuda_graph, pdl, kw):
     if not use_cuda_graph:
         return _search_loop(engine, px, **kw)
-    key = (tuple(px.shape),) + tuple(sorted(kw.items()))
+    key = (tuple(px.shape), pdl) + tuple(sorted(kw.items()))
     graphs = engine.__dict__.setdefault("_gen_graphs", {})
     entry = graphs.get(key)
     if entry is None:

@@ -153,6 +153,11 @@ def residual_ln_fwd(acc, bias, x, gamma, beta, eps, out):
     return out
 
 
+def launch_options(pdl=-1, gemm_b_static=-1):
+    """mic_launch_options: programmatic dependent launch on/off, weights-are-static hint for the decode loop."""
+    lib().mic_launch_options(int(pdl), int(gemm_b_static))
+
+
 _COUNTERS = {}
 
 
