@@ -153,6 +153,59 @@ int mic_decode_attention(void* stream, const void* q, long long ldq, const void*
                          long long ldkv, const int* ancestors, int cache_len, int n_keys, int rows_per_kv, void* o,
                          long long ldo, int R, int H, int head_dim, float scale);
 
+/* ---- persistent decoder step (cached decode) -----------------------------------------------
+ * One launch runs all layers of FlaxMBartDecoderLayer (pre-LN mBART; modeling_clip_vision_mbart.py:519-651 with
+ * past_key_values) for one new token per row:  self_attn_layer_norm of layer 0, then per layer  q|k|v projection
+ * (k|v written straight into position `pos` of the layer's cache) -> cached self-attention through the beam
+ * ancestor table -> out_proj -> residual + encoder_attn_layer_norm -> cross-attention query -> attention over the
+ * image's visual K/V -> out_proj -> residual + final_layer_norm -> fc1 + activation -> fc2 -> residual + the NEXT
+ * block's LayerNorm (the decoder's layer_norm after the last layer).
+ * One CTA per SM stays resident; the ops are phases separated by a grid barrier, and the producer streams the
+ * next phase's weights while the current one drains.  Weights are consumed from a re-packed copy (8 KB tiles that
+ * are the shared-memory image of the tcgen05 operand; mic_decoder_pack_weights, to be re-run whenever the
+ * parameters change).  Caller provides (and keeps alive) every buffer.
+ *   before the call:  buffers.x = residual stream after layernorm_embedding (row-major bf16 [R, d])
+ *   after  the call:  buffers.h_out = hidden state after the decoder layer_norm (row-major) -> lm_head input */
+typedef struct {
+  const float* ln_sa_g; const float* ln_sa_b;      /* self_attn_layer_norm                      */
+  const void* sa_qkv_w; const float* sa_qkv_b;     /* [d, 3d] bf16 (in, out), [3d]              */
+  const void* sa_o_w;   const float* sa_o_b;       /* [d, d], [d]                               */
+  const float* ln_ca_g; const float* ln_ca_b;      /* encoder_attn_layer_norm                   */
+  const void* ca_q_w;   const float* ca_q_b;
+  const void* ca_o_w;   const float* ca_o_b;
+  const float* ln_f_g;  const float* ln_f_b;       /* final_layer_norm (before the FFN)         */
+  const void* fc1_w;    const float* fc1_b;        /* [d, ffn], [ffn]                           */
+  const void* fc2_w;    const float* fc2_b;        /* [ffn, d], [d]                             */
+  void* self_kv;                                   /* [R, cache_len, 2d] bf16: k | v            */
+  const void* enc_k;    const void* enc_v;         /* visual K / V of this layer, row pitch ld_enc */
+} mic_decoder_layer_t;
+typedef struct {
+  void* x; void* q;                                /* bf16 [R, d] row-major                     */
+  void* a_tiles; void* o_tiles;                    /* bf16 [ceil(R/128)*128, d]  tile-image scratch, 1024-B aligned */
+  void* g_tiles;                                   /* bf16 [ceil(R/128)*128, ffn] tile-image scratch            */
+  float* acc; float* q_acc;                        /* fp32 [R, d], zero before the first step (kept zero by the kernel) */
+  const int* ancestors;                            /* [R, cache_len] beam ancestor table or NULL */
+  void* h_out;                                     /* bf16 [R, d] row-major result              */
+  const float* ln_out_g; const float* ln_out_b;    /* decoder layer_norm                        */
+} mic_decoder_buffers_t;
+long long mic_decoder_plan_bytes(int num_layers);
+long long mic_decoder_packed_bytes(int num_layers, int d_model, int ffn_dim);
+/* re-pack the six projection kernels of every layer into `packed` (1024-byte aligned, mic_decoder_packed_bytes).
+ * Capturable; generate() runs it once per call so that updated parameters are always picked up. */
+int mic_decoder_pack_weights(void* stream, const mic_decoder_layer_t* layers, int num_layers, int d_model,
+                             int ffn_dim, void* packed);
+/* builds the phase table on the host and copies it to plan_dev (128-byte aligned device buffer of
+ * mic_decoder_plan_bytes).  Not capturable into a CUDA graph (host staging): call once per buffer set. */
+int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_decoder_layer_t* layers, int num_layers,
+                          const mic_decoder_buffers_t* buffers, const void* packed, int R, int d_model, int heads,
+                          int ffn_dim, int cache_len, int enc_tokens, int rows_per_image, long long ld_enc, int act,
+                          float eps);
+/* sync_counter: one uint32, zero before the first call (the kernel leaves it zero).  Capturable.
+ * phase_times (optional, NULL = off): [1 + 11 * num_layers, #SMs] (+256 trace slots) %globaltimer stamp of each
+ * CTA's arrival at the end of each phase (profiling aid: tools/profile_decoder_step.py). */
+int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, int pos, unsigned int* sync_counter,
+                     unsigned long long* phase_times);
+
 /* ---- search steps (generation_clip_vision_utils.py) ---------------------------------------------------
  * merge the lm_head_search slab partials: per row log-softmax normaliser + top-8 (log-prob, token) */
 int mic_search_merge(void* stream, const float* pmax, const float* psum, const float* cand_val, const int* cand_idx,

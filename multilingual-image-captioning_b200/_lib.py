@@ -19,6 +19,11 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "mic_abi_version": [],
     "mic_launch_options": [I, I],
+    "mic_decoder_plan_bytes": [I],
+    "mic_decoder_packed_bytes": [I, I, I],
+    "mic_decoder_pack_weights": [P, P, I, I, I, P],
+    "mic_decoder_plan_init": [P, P, P, I, P, P, I, I, I, I, I, I, I, L, I, F],
+    "mic_decoder_step": [P, P, I, I, I, P, P],
     "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I, P, I, F],
     "mic_lm_head_num_partials": [I],
     "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P, P, L],
@@ -85,7 +90,7 @@ def lib() -> C.CDLL:
     for name, args in SIGNATURES.items():
         fn = getattr(l, name)       # AttributeError if the symbol is not exported -> loud
         fn.argtypes = args
-        fn.restype = L if name.endswith("_workspace_floats") else I
+        fn.restype = L if name.endswith(("_workspace_floats", "_plan_bytes", "_packed_bytes")) else I
     l.mic_last_error.argtypes = []
     l.mic_last_error.restype = C.c_char_p
     if l.mic_abi_version() != 1:

@@ -7,12 +7,14 @@
 // Semantics = flax dot_product_attention_weights as used by FlaxCLIPAttention / FlaxMBartAttention:
 // scores = (q/sqrt(64)) . k ; additive mask 0/-inf from (causal AND key padding) ; softmax ; . v
 #include "common.cuh"
+#include "decode_device.cuh"
 
 #include "../../include/mic_b200.h"
 
 namespace {
 
-constexpr int HD = 64;     // head dim
+using micdec::HD;          // head dim 64
+using micdec::DecAttnArgs;
 constexpr int TMAX = 64;   // max queries / keys per (batch, head) tile
 constexpr int LDS = 72;    // smem row pitch in bf16 (144 B: conflict-free fragment loads)
 
@@ -703,29 +705,8 @@ __global__ void __launch_bounds__(128) attention_bwd_dkv_kernel(const AttnArgs a
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cached decode attention (1 query token per row), SURVEY.md A.3.
-// Self-attention reads the K/V history of a beam through an ancestor table instead of physically
-// reordering the cache (generation_clip_vision_utils.py:945-953 gathers 24 arrays every step):
-//   slot(r, j) = anc[r*T + j]  = cache row that holds position j of beam-row r's history
-// Cross-attention: K/V of the S visual tokens, shared by the beams of an image (row r -> r / beams).
-// One warp per (row, head); lanes split keys for the scores and head-dim for the output.
-// ---------------------------------------------------------------------------------------------
-struct DecAttnArgs {
-  const bf16* q;         // [R, ldq] (head h at h*64)
-  long long ldq;
-  const bf16 *kc, *vc;   // cache base: element (row, pos, h, d) at ((row*T + pos) * ldkv + h*64 + d)
-  long long ldkv;
-  const int* anc;        // [R, T] ancestor rows or null (identity)
-  int T;                 // cache length (positions per row)
-  int n_keys;            // keys to attend (cur position + 1) or S for cross
-  int rows_per_kv;       // cross-attention: beams per image (kv row = r / rows_per_kv); 1 otherwise
-  bf16* o;               // [R, ldo]
-  long long ldo;
-  int R, H;
-  float scale;
-};
-
+// Cached decode attention: one warp per (row, head); body shared with the persistent decoder-step kernel
+// (decode_device.cuh).
 __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -734,95 +715,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int wid = blockIdx.x * 4 + w;
   if (wid >= a.R * a.H) return;
-  const int r = wid / a.H, h = wid % a.H;
-  const int nk = a.n_keys;
-  // cache rows of the visible history (ancestor table) or the shared visual K/V row
-  const int kvrow_default = r / a.rows_per_kv;
-  for (int j = lane; j < nk; j += 32) s_row[w][j] = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
-  // q in registers: every lane holds the full 64-d query, pre-scaled
-  float qv[HD];
-  {
-    const bf16* qp = a.q + (long long)r * a.ldq + h * HD;
-#pragma unroll
-    for (int c = 0; c < HD; c += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(qp + c);
-      const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(uu[j]);
-        qv[c + 2 * j] = f.x * a.scale;
-        qv[c + 2 * j + 1] = f.y * a.scale;
-      }
-    }
-  }
-  __syncwarp();
-  // scores: lane handles keys lane, lane+32, ... (8 independent 16-byte loads per key)
-  float mx = -INFINITY;
-  float sc[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int j = lane + i * 32;
-    float sdot = -INFINITY;
-    if (j < nk) {
-      const bf16* kp = a.kc + ((long long)s_row[w][j] * a.T + j) * a.ldkv + h * HD;
-      uint4 kk[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kk[c] = *reinterpret_cast<const uint4*>(kp + c * 8);
-      float acc = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&kk[c]);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const float2 f = unpack_bf16(uu[jj]);
-          acc = fmaf(qv[c * 8 + 2 * jj], f.x, acc);
-          acc = fmaf(qv[c * 8 + 2 * jj + 1], f.y, acc);
-        }
-      }
-      sdot = acc;
-    }
-    sc[i] = sdot;
-    mx = fmaxf(mx, sdot);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int j = lane + i * 32;
-    const float p = (j < nk) ? __expf(sc[i] - mx) : 0.f;
-    if (j < nk) s_p[w][j] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.0f / sum;
-  __syncwarp();
-  // P.V: 4 key groups x 8 dim groups; lane (kg, dl) accumulates dims dl*8..dl*8+7 over keys kg, kg+4, ...
-  const int kg = lane >> 3, dl = lane & 7;
-  float o[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = 0.f;
-  for (int j = kg; j < nk; j += 4) {
-    const bf16* vp = a.vc + ((long long)s_row[w][j] * a.T + j) * a.ldkv + h * HD + dl * 8;
-    const uint4 u = *reinterpret_cast<const uint4*>(vp);
-    const float p = s_p[w][j];
-    const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const float2 f = unpack_bf16(uu[jj]);
-      o[2 * jj] = fmaf(p, f.x, o[2 * jj]);
-      o[2 * jj + 1] = fmaf(p, f.y, o[2 * jj + 1]);
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
-    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
-  }
-  if (kg == 0) {
-    *reinterpret_cast<uint4*>(a.o + (long long)r * a.ldo + h * HD + dl * 8) =
-        make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
-                   pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
-  }
+  micdec::decode_attn_item(a, wid / a.H, wid % a.H, s_p[w], s_row[w], lane);
 }
 
 }  // namespace
@@ -920,7 +813,7 @@ extern "C" int mic_decode_attention(void* stream, const void* q, long long ldq, 
   DecAttnArgs a;
   a.q = (const bf16*)q; a.ldq = ldq; a.kc = (const bf16*)k_cache; a.vc = (const bf16*)v_cache; a.ldkv = ldkv;
   a.anc = ancestors; a.T = cache_len; a.n_keys = n_keys; a.rows_per_kv = rows_per_kv < 1 ? 1 : rows_per_kv;
-  a.o = (bf16*)o; a.ldo = ldo; a.R = R; a.H = H; a.scale = scale;
+  a.o = (bf16*)o; a.ldo = ldo; a.R = R; a.H = H; a.scale = scale; a.q_acc = nullptr; a.q_bias = nullptr; a.o_tiled_kb = 0;
   MIC_CHECK_CUDA(mic_launch(decode_attention_kernel, dim3((R * H + 3) / 4), dim3(128), 0, STREAM, a));
   return MIC_OK;
 }

@@ -1,0 +1,423 @@
+// Device-side building blocks of the cached decoder step, shared by the stand-alone kernels
+// (attention.cu / elementwise.cu) and the persistent decoder-step kernel (decoder_step.cu).
+#pragma once
+#include "common.cuh"
+
+namespace micdec {
+
+constexpr int HD = 64;            // head dim
+constexpr int LN_MAX_ITERS = 4;   // features <= 1024 (32 lanes * 8 elements * 4)
+
+__device__ __forceinline__ void load8(const bf16* p, float* x) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
+  f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
+  f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
+  f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float* x) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                            pack_bf16(x[6], x[7]));
+}
+__device__ __forceinline__ void load8f(const float* p, float* x) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+// L2-coherent variants (ld.global.cg): data another SM wrote earlier in the SAME launch must not be served
+// from this SM's L1
+__device__ __forceinline__ void load8_cg(const bf16* p, float* x) {
+  const uint4 u = __ldcg(reinterpret_cast<const uint4*>(p));
+  float2 f;
+  f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
+  f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
+  f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
+  f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
+}
+__device__ __forceinline__ void load8f_cg(const float* p, float* x) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldcg(reinterpret_cast<const float4*>(p + 4));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+
+// "UMMA tile image" layout of a K-major bf16 activation matrix [rows, cols]: 128-row x 64-column tiles, each a
+// contiguous 16 KB block that is exactly the SWIZZLE_128B shared-memory image tcgen05.mma reads (row r of the tile at
+// r*128 B, its 16-byte chunk c stored at chunk c ^ (r & 7)); tiles ordered [row tile][k block].  A consumer fetches a
+// whole operand stage with ONE bulk copy instead of a 128-row TMA box.  Returns the element offset of (row, col),
+// col % 8 == 0; tiled_kb = cols / 64.
+__device__ __forceinline__ long long tiled_off(int row, int col, int tiled_kb) {
+  const int r = row & 127, c = (col & 63) >> 3;
+  return ((long long)(row >> 7) * tiled_kb + (col >> 6)) * 8192 + r * 64 + ((c ^ (r & 7)) << 3);
+}
+
+// flax.linen.LayerNorm statistics: mean, E[x^2] - mean^2 (clamped at 0), biased
+__device__ __forceinline__ void ln_stats(const float (*x)[8], int d, int lane, float* mean, float* rstd, float eps) {
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    if (lane * 8 + it * 256 < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += x[it][j];
+        s2 += x[it][j] * x[it][j];
+      }
+    }
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float m = s / d;
+  const float var = fmaxf(s2 / d - m * m, 0.f);
+  *mean = m;
+  *rstd = rsqrtf(var + eps);
+}
+
+// x[row] += acc[row] + bias ; y[row] = LayerNorm(x[row]) ; acc[row] = 0.      One warp per row.
+// kCoherent: acc/x were produced by other SMs during this launch (persistent kernel) -> L2 loads.
+template <bool kCoherent>
+__device__ __forceinline__ void residual_ln_row(float* __restrict__ acc, const float* __restrict__ bias,
+                                                bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps, bf16* __restrict__ y,
+                                                int row, int d, int lane, int y_tiled_kb = 0) {
+  float v[LN_MAX_ITERS][8];
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float a[8], b[8];
+      if (kCoherent) {
+        load8_cg(x + (long long)row * d + c, v[it]);
+        load8f_cg(acc + (long long)row * d + c, a);
+      } else {
+        load8(x + (long long)row * d + c, v[it]);
+        load8f(acc + (long long)row * d + c, a);
+      }
+      load8f(bias + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[it][j] = bf16_round(v[it][j] + a[j] + b[j]);
+      store8(x + (long long)row * d + c, v[it]);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(acc + (long long)row * d + c) = z;
+      *reinterpret_cast<float4*>(acc + (long long)row * d + c + 4) = z;
+    }
+  }
+  float mean, rstd;
+  ln_stats(v, d, lane, &mean, &rstd, eps);
+#pragma unroll
+  for (int it = 0; it < LN_MAX_ITERS; ++it) {
+    const int c = lane * 8 + it * 256;
+    if (c < d) {
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + b[j];
+      store8(y + (y_tiled_kb ? tiled_off(row, c, y_tiled_kb) : (long long)row * d + c), o);
+    }
+  }
+}
+
+// Same op, written for CODE SIZE (persistent kernel: every phase starts on a cold instruction cache, so straight-
+// line unrolled code costs an L2 round trip per 128 bytes of SASS): two rolled passes, the second re-reads the
+// row it just wrote instead of keeping it in registers.
+__device__ __forceinline__ void residual_ln_row_lean(float* __restrict__ acc, const float* __restrict__ bias,
+                                                     bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, bf16* __restrict__ y,
+                                                     int row, int d, int lane, int y_tiled_kb,
+                                                     unsigned long long* trace = nullptr) {
+  float s = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int c = lane * 8; c < d; c += 256) {
+    float v[8], a[8], b[8];
+    load8_cg(x + (long long)row * d + c, v);
+    if (trace && c == lane * 8) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[0]) : "f"(v[0])); }
+    load8f_cg(acc + (long long)row * d + c, a);
+    if (trace && c == lane * 8) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[1]) : "f"(a[0])); }
+    load8f(bias + c, b);
+    if (trace && c == lane * 8) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2]) : "f"(b[0])); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = bf16_round(v[j] + a[j] + b[j]);
+      s += v[j];
+      s2 += v[j] * v[j];
+    }
+    store8(x + (long long)row * d + c, v);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(acc + (long long)row * d + c) = z;
+    *reinterpret_cast<float4*>(acc + (long long)row * d + c + 4) = z;
+  }
+  if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[3]) : "f"(s)); }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float mean = s / d;
+  const float rstd = rsqrtf(fmaxf(s2 / d - mean * mean, 0.f) + eps);
+  if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[4]) : "f"(rstd)); }
+#pragma unroll 1
+  for (int c = lane * 8; c < d; c += 256) {
+    float v[8], g[8], b[8], o[8];
+    load8_cg(x + (long long)row * d + c, v);        // this thread's own store, read back through L2
+    load8f(gamma + c, g);
+    load8f(beta + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * g[j] + b[j];
+    store8(y + (y_tiled_kb ? tiled_off(row, c, y_tiled_kb) : (long long)row * d + c), o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cached decode attention (1 query token per row), SURVEY.md A.3.
+// Self-attention reads the K/V history of a beam through an ancestor table instead of physically
+// reordering the cache (generation_clip_vision_utils.py:945-953 gathers 24 arrays every step):
+//   slot(r, j) = anc[r*T + j]  = cache row that holds position j of beam-row r's history
+// Cross-attention: K/V of the S visual tokens, shared by the beams of an image (row r -> r / beams).
+// One warp per (row, head); lanes split keys for the scores and head-dim for the output.
+// ---------------------------------------------------------------------------------------------
+struct DecAttnArgs {
+  const bf16* q;         // [R, ldq] (head h at h*64)
+  long long ldq;
+  const bf16 *kc, *vc;   // cache base: element (row, pos, h, d) at ((row*T + pos) * ldkv + h*64 + d)
+  long long ldkv;
+  const int* anc;        // [R, T] ancestor rows or null (identity)
+  int T;                 // cache length (positions per row)
+  int n_keys;            // keys to attend (cur position + 1) or S for cross (<= 128)
+  int rows_per_kv;       // cross-attention: beams per image (kv row = r / rows_per_kv); 1 otherwise
+  bf16* o;               // [R, ldo]
+  long long ldo;
+  int R, H;
+  float scale;
+  // persistent-kernel variant: q = bf16(q_acc + q_bias) taken from an fp32 split-K accumulator that is zeroed
+  // again once read (q == nullptr then)
+  float* q_acc;
+  const float* q_bias;
+  int o_tiled_kb;        // > 0: o is written in the UMMA tile image layout (tiled_off), = H
+};
+
+// s_p: 128 floats, s_row: 128 ints of per-warp shared scratch.  q / k / v go through L2 (ld.global.cg): in the
+// persistent kernel the newest position was written by another SM within the same launch.
+__device__ __forceinline__ void decode_attn_item(const DecAttnArgs& a, int r, int h, float* s_p, int* s_row,
+                                                 int lane) {
+  const int nk = a.n_keys;
+  const int kvrow_default = r / a.rows_per_kv;
+  for (int j = lane; j < nk; j += 32) s_row[j] = a.anc ? a.anc[(long long)r * a.T + j] : kvrow_default;
+  // q in registers: every lane holds the full 64-d query, pre-scaled
+  float qv[HD];
+  if (a.q != nullptr) {
+    const bf16* qp = a.q + (long long)r * a.ldq + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      float f[8];
+      load8_cg(qp + c, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qv[c + j] = f[j] * a.scale;
+    }
+  } else {
+    float* qa = a.q_acc + (long long)r * a.ldq + h * HD;
+    const float* qb = a.q_bias + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      float f[8], b[8];
+      load8f_cg(qa + c, f);
+      load8f(qb + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qv[c + j] = bf16_round(f[j] + b[j]) * a.scale;
+    }
+    __syncwarp();
+    // hand the accumulator back zeroed (each lane clears 2 of the 64 floats)
+    *reinterpret_cast<float2*>(qa + lane * 2) = make_float2(0.f, 0.f);
+  }
+  __syncwarp();
+  // scores: lane handles keys lane, lane+32, ... (8 independent 16-byte loads per key)
+  float mx = -INFINITY;
+  float sc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = lane + i * 32;
+    float sdot = -INFINITY;
+    if (j < nk) {
+      const bf16* kp = a.kc + ((long long)s_row[j] * a.T + j) * a.ldkv + h * HD;
+      uint4 kk[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kk[c] = __ldcg(reinterpret_cast<const uint4*>(kp + c * 8));
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&kk[c]);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 f = unpack_bf16(uu[jj]);
+          acc = fmaf(qv[c * 8 + 2 * jj], f.x, acc);
+          acc = fmaf(qv[c * 8 + 2 * jj + 1], f.y, acc);
+        }
+      }
+      sdot = acc;
+    }
+    sc[i] = sdot;
+    mx = fmaxf(mx, sdot);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = lane + i * 32;
+    const float p = (j < nk) ? __expf(sc[i] - mx) : 0.f;
+    if (j < nk) s_p[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __syncwarp();
+  // P.V: 4 key groups x 8 dim groups; lane (kg, dl) accumulates dims dl*8..dl*8+7 over keys kg, kg+4, ...
+  const int kg = lane >> 3, dl = lane & 7;
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int j = kg; j < nk; j += 4) {
+    const bf16* vp = a.vc + ((long long)s_row[j] * a.T + j) * a.ldkv + h * HD + dl * 8;
+    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(vp));
+    const float p = s_p[j];
+    const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float2 f = unpack_bf16(uu[jj]);
+      o[2 * jj] = fmaf(p, f.x, o[2 * jj]);
+      o[2 * jj + 1] = fmaf(p, f.y, o[2 * jj + 1]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (kg == 0) {
+    bf16* dst = a.o + (a.o_tiled_kb ? tiled_off(r, h * HD + dl * 8, a.o_tiled_kb) : (long long)r * a.ldo + h * HD + dl * 8);
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                   pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
+  }
+  __syncwarp();   // scratch is reused by the warp's next item
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged variant for the persistent kernel, where only 8 warps per SM are available to hide latency: ALL K and V
+// rows of an item are pulled into a per-warp 16 KB shared-memory stage with 16-byte cp.async copies issued at once
+// (one round trip instead of a dependent chain), and an item covers the `rows_per_kv` query rows that share the
+// same K/V (cross-attention: the beams of an image), so shared K/V are read once.  n_keys <= 64.
+//   kv_smem: K row j at j*128, V row j at 8192 + j*128; 16-byte chunk c of row j is stored at chunk c ^ (j & 7)
+//   q_smem : [rows_per_kv (<= 4), 64] pre-scaled queries;   p_smem: [64] softmax numerators
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_attn_group_staged(const DecAttnArgs& a, int kv_item, int h, uint8_t* kv_smem,
+                                                         float* q_smem, float* p_smem, int lane) {
+  const int nk = a.n_keys;
+  const int rpk = a.rows_per_kv;
+  const int r0 = kv_item * rpk;
+  int row0 = kv_item, row1 = kv_item;          // cache rows of keys lane, lane + 32
+  if (a.anc) {
+    row0 = lane < nk ? a.anc[(long long)r0 * a.T + lane] : 0;
+    row1 = lane + 32 < nk ? a.anc[(long long)r0 * a.T + 32 + lane] : 0;
+  }
+  const uint32_t kv_base = smem_u32(kv_smem);
+  const int total = nk * 16;
+  for (int base = 0; base < total; base += 32) {
+    const int idx = base + lane;
+    const int j = idx >> 4, c = idx & 15;
+    const int rj0 = __shfl_sync(0xffffffffu, row0, j & 31), rj1 = __shfl_sync(0xffffffffu, row1, j & 31);
+    if (idx < total) {
+      const int rj = j < 32 ? rj0 : rj1;
+      const int cc = c & 7;
+      const bf16* src = (c < 8 ? a.kc : a.vc) + ((long long)rj * a.T + j) * a.ldkv + h * HD + cc * 8;
+      cp_async_16(kv_base + (c < 8 ? 0 : 8192) + j * 128 + ((cc ^ (j & 7)) << 4), src);
+    }
+  }
+  cp_async_commit();
+  // queries of the item's rows -> smem, pre-scaled (8 floats per lane, lanes >= 8*rpk idle)
+  if (lane < 8 * rpk && r0 + (lane >> 3) < a.R) {
+    const int rr = lane >> 3, c8 = (lane & 7) * 8;
+    const int r = r0 + rr;
+    float f[8];
+    if (a.q != nullptr) {
+      load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
+    } else {
+      float* qa = a.q_acc + (long long)r * a.ldq + h * HD + c8;
+      float b[8];
+      load8f_cg(qa, f);
+      load8f(a.q_bias + h * HD + c8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] + b[j]);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(qa) = z;                  // hand the split-K accumulator back zeroed
+      *reinterpret_cast<float4*>(qa + 4) = z;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q_smem[rr * HD + c8 + j] = f[j] * a.scale;
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  const int kg = lane >> 3, dl = lane & 7;
+  for (int rr = 0; rr < rpk; ++rr) {
+    const int r = r0 + rr;
+    if (r >= a.R) break;
+    const float4* q4 = reinterpret_cast<const float4*>(q_smem + rr * HD);
+    float sc[2];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = lane + t * 32;
+      float acc = -INFINITY;
+      if (j < nk) {
+        acc = 0.f;
+        const uint8_t* krow = kv_smem + j * 128;
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+          const uint4 kk = *reinterpret_cast<const uint4*>(krow + ((c ^ (j & 7)) << 4));
+          const float4 qa = q4[2 * c], qb = q4[2 * c + 1];
+          float2 f;
+          f = unpack_bf16(kk.x); acc = fmaf(qa.x, f.x, acc); acc = fmaf(qa.y, f.y, acc);
+          f = unpack_bf16(kk.y); acc = fmaf(qa.z, f.x, acc); acc = fmaf(qa.w, f.y, acc);
+          f = unpack_bf16(kk.z); acc = fmaf(qb.x, f.x, acc); acc = fmaf(qb.y, f.y, acc);
+          f = unpack_bf16(kk.w); acc = fmaf(qb.z, f.x, acc); acc = fmaf(qb.w, f.y, acc);
+        }
+      }
+      sc[t] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = lane + t * 32;
+      const float p = (j < nk) ? __expf(sc[t] - mx) : 0.f;
+      if (j < nk) p_smem[j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    for (int j = kg; j < nk; j += 4) {
+      const uint4 u = *reinterpret_cast<const uint4*>(kv_smem + 8192 + j * 128 + ((dl ^ (j & 7)) << 4));
+      const float p = p_smem[j];
+      float2 f;
+      f = unpack_bf16(u.x); o[0] = fmaf(p, f.x, o[0]); o[1] = fmaf(p, f.y, o[1]);
+      f = unpack_bf16(u.y); o[2] = fmaf(p, f.x, o[2]); o[3] = fmaf(p, f.y, o[3]);
+      f = unpack_bf16(u.z); o[4] = fmaf(p, f.x, o[4]); o[5] = fmaf(p, f.y, o[5]);
+      f = unpack_bf16(u.w); o[6] = fmaf(p, f.x, o[6]); o[7] = fmaf(p, f.y, o[7]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+      o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+    }
+    if (kg == 0) {
+      bf16* dst = a.o + (a.o_tiled_kb ? tiled_off(r, h * HD + dl * 8, a.o_tiled_kb) : (long long)r * a.ldo + h * HD + dl * 8);
+      *reinterpret_cast<uint4*>(dst) =
+          make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                     pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
+    }
+    __syncwarp();   // p_smem is rewritten by the next row
+  }
+  __syncwarp();     // the stage is refilled by the warp's next item
+}
+
+}  // namespace micdec

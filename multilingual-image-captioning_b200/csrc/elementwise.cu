@@ -2,51 +2,13 @@
 // activation backward + bias-gradient column sums, CE finalisation, AdamW.  All use 16-byte vector
 // access on the contiguous feature dimension and warp-shuffle reductions; fp32 statistics.
 #include "common.cuh"
+#include "decode_device.cuh"
 
 #include "../../include/mic_b200.h"
 
 namespace {
 
-constexpr int LN_MAX_ITERS = 4;   // features <= 1024 (32 lanes * 8 elements * 4)
-
-__device__ __forceinline__ void load8(const bf16* p, float* x) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  float2 f;
-  f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
-  f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
-  f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
-  f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
-}
-__device__ __forceinline__ void store8(bf16* p, const float* x) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                            pack_bf16(x[6], x[7]));
-}
-__device__ __forceinline__ void load8f(const float* p, float* x) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-}
-
-// flax.linen.LayerNorm statistics: mean, E[x^2] - mean^2 (clamped at 0), biased
-__device__ __forceinline__ void ln_stats(const float (*x)[8], int d, int lane, float* mean, float* rstd, float eps) {
-  float s = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int it = 0; it < LN_MAX_ITERS; ++it) {
-    if (lane * 8 + it * 256 < d) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s += x[it][j];
-        s2 += x[it][j] * x[it][j];
-      }
-    }
-  }
-  s = warp_sum(s);
-  s2 = warp_sum(s2);
-  const float m = s / d;
-  const float var = fmaxf(s2 / d - m * m, 0.f);
-  *mean = m;
-  *rstd = rsqrtf(var + eps);
-}
+using namespace micdec;
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm forward.  One warp per row.
@@ -100,37 +62,7 @@ residual_ln_fwd_kernel(float* __restrict__ acc, const float* __restrict__ bias, 
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
-  float v[LN_MAX_ITERS][8];
-#pragma unroll
-  for (int it = 0; it < LN_MAX_ITERS; ++it) {
-    const int c = lane * 8 + it * 256;
-    if (c < d) {
-      float a[8], b[8];
-      load8(x + (long long)row * d + c, v[it]);
-      load8f(acc + (long long)row * d + c, a);
-      load8f(bias + c, b);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[it][j] = bf16_round(v[it][j] + a[j] + b[j]);
-      store8(x + (long long)row * d + c, v[it]);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(acc + (long long)row * d + c) = z;
-      *reinterpret_cast<float4*>(acc + (long long)row * d + c + 4) = z;
-    }
-  }
-  float mean, rstd;
-  ln_stats(v, d, lane, &mean, &rstd, eps);
-#pragma unroll
-  for (int it = 0; it < LN_MAX_ITERS; ++it) {
-    const int c = lane * 8 + it * 256;
-    if (c < d) {
-      float g[8], b[8], o[8];
-      load8f(gamma + c, g);
-      load8f(beta + c, b);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mean) * rstd * g[j] + b[j];
-      store8(y + (long long)row * d + c, o);
-    }
-  }
+  residual_ln_row<false>(acc, bias, x, gamma, beta, eps, y, row, d, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

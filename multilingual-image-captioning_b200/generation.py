@@ -30,9 +30,11 @@ class DecodeCache:
         self.self_kv = engine.bufs.get("gen.self_kv", (t.decoder_layers, rows, max_length, 2 * t.d_model))
         self.enc_kv = enc_kv
         self.ancestors = None
-        if use_ancestors:
-            self.ancestors = torch.arange(rows, dtype=I32, device=dev)[:, None].expand(rows, max_length).contiguous()
+        if use_ancestors:       # stable address (the fused decoder plan holds it): refilled in place
+            self.ancestors = engine.bufs.get("gen.ancestors", (rows, max_length), I32)
+            self.ancestors.copy_(torch.arange(rows, dtype=I32, device=dev)[:, None].expand(rows, max_length))
         self.index = 0
+        self.fused = None
 
 
 def decode_step(engine, cache: DecodeCache, tokens, pos: int):
@@ -91,6 +93,85 @@ def decode_step(engine, cache: DecodeCache, tokens, pos: int):
     return a
 
 
+def _aligned(engine, name, nbytes, align=1024):
+    """Cached uint8 device buffer with an aligned start (tile-image buffers are bulk-copy sources)."""
+    raw = engine.bufs.get(name, (nbytes + align,), torch.uint8)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + nbytes]
+
+
+def _fused_plan(engine, cache: DecodeCache):
+    """Phase table of the persistent decoder-step kernel for this buffer set (built once per buffer set)."""
+    t, ps, b = engine.t, engine.ps, engine.bufs
+    R, d, T, L = cache.rows, t.d_model, cache.T, t.decoder_layers
+    F = t.decoder_ffn_dim
+    Rp = (R + 127) // 128 * 128
+    bufs = {"x": b.get("gen.x", (R, d)), "q": b.get("gen.q", (R, d)), "h_out": b.get("gen.a", (R, d)),
+            "a_tiles": _aligned(engine, "gen.a_tiles", Rp * d * 2), "o_tiles": _aligned(engine, "gen.o_tiles", Rp * d * 2),
+            "g_tiles": _aligned(engine, "gen.g_tiles", Rp * F * 2), "ancestors": cache.ancestors,
+            "ln_out_g": ps.f("d.ln_final.scale"), "ln_out_b": ps.f("d.ln_final.bias")}
+    for n in ("acc", "q_acc"):
+        z = b.t.get("gen." + n)
+        if z is None or tuple(z.shape) != (R, d):
+            z = torch.zeros((R, d), dtype=F32, device=engine.dev)     # zeroed once; the kernel hands it back zeroed
+            b.t["gen." + n] = z
+        bufs[n] = z
+    packed = _aligned(engine, "gen.wpack", ops.decoder_packed_bytes(L, d, F))
+    key = (R, T, cache.rows_per_image, cache.enc_kv.data_ptr(), cache.self_kv.data_ptr(), ps.shadow.data_ptr(),
+           ps.master.data_ptr(), packed.data_ptr()) + tuple(0 if v is None else v.data_ptr() for v in bufs.values())
+    plans = engine.__dict__.setdefault("_fused_plans", {})
+    entry = plans.get("decoder")
+    if entry is not None and entry[0] == key:
+        return entry[1]
+    assert not torch.cuda.is_current_stream_capturing(), "fused decoder plan must be built before graph capture"
+    layers = []
+    for l in range(L):
+        n = f"d.{l}"
+        layers.append({
+            "ln_sa_g": ps.f(n + ".ln_sa.scale"), "ln_sa_b": ps.f(n + ".ln_sa.bias"),
+            "sa_qkv_w": ps.w(n + ".sa_qkv.w"), "sa_qkv_b": ps.f(n + ".sa_qkv.b"),
+            "sa_o_w": ps.w(n + ".sa_o.w"), "sa_o_b": ps.f(n + ".sa_o.b"),
+            "ln_ca_g": ps.f(n + ".ln_ca.scale"), "ln_ca_b": ps.f(n + ".ln_ca.bias"),
+            "ca_q_w": ps.w(n + ".ca_q.w"), "ca_q_b": ps.f(n + ".ca_q.b"),
+            "ca_o_w": ps.w(n + ".ca_o.w"), "ca_o_b": ps.f(n + ".ca_o.b"),
+            "ln_f_g": ps.f(n + ".ln_f.scale"), "ln_f_b": ps.f(n + ".ln_f.bias"),
+            "fc1_w": ps.w(n + ".fc1.w"), "fc1_b": ps.f(n + ".fc1.b"),
+            "fc2_w": ps.w(n + ".fc2.w"), "fc2_b": ps.f(n + ".fc2.b"),
+            "self_kv": cache.self_kv[l],
+            "enc_k": cache.enc_kv[:, l * 2 * d: l * 2 * d + d], "enc_v": cache.enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]})
+    lstruct = ops.decoder_layers_struct(layers)
+    plan = torch.empty(ops.decoder_plan_bytes(L) + 128, dtype=torch.uint8, device=engine.dev)
+    plan = plan[(-plan.data_ptr()) % 128:]
+    sync = torch.zeros(1, dtype=I32, device=engine.dev)
+    for n in ("a_tiles", "o_tiles", "g_tiles"):
+        bufs[n].zero_()                                   # rows beyond R of the last row tile stay finite
+    ops.decoder_plan_init(plan, lstruct, bufs, packed, R, d, t.decoder_attention_heads, F, T, engine.c.num_tokens,
+                          cache.rows_per_image, L * 2 * d, t.activation_function, t.layer_norm_eps)
+    fp = {"plan": plan, "sync": sync, "bufs": bufs, "layers": lstruct, "packed": packed}
+    plans["decoder"] = (key, fp)
+    return fp
+
+
+def fused_prepare(engine, cache: DecodeCache):
+    """Once per generate() call: (re)build the plan if the buffers moved and re-pack the current weights."""
+    t = engine.t
+    fp = _fused_plan(engine, cache)
+    ops.decoder_pack_weights(fp["layers"], t.d_model, t.decoder_ffn_dim, fp["packed"])
+    return fp
+
+
+def decode_step_fused(engine, cache: DecodeCache, tokens, pos: int, fp=None):
+    """decode_step with all decoder layers in ONE persistent kernel (csrc/decoder_step.cu)."""
+    t, ps = engine.t, engine.ps
+    assert t.pre_layernorm and t.final_layer_norm, "fused cached decode is wired for the pre-LN (mBART) decoder"
+    if fp is None:
+        fp = fused_prepare(engine, cache)
+    ops.embed_ln_fwd(tokens, None, 1, pos + t.position_offset, ps.w("shared"), ps.w("d.pos"), engine.emb_scale,
+                     ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), t.layer_norm_eps, None, fp["bufs"]["x"])
+    ops.decoder_step(fp["plan"], t.decoder_layers, cache.rows, pos, fp["sync"])
+    return fp["bufs"]["h_out"]
+
+
 def _search_ws(engine, R):
     b, V = engine.bufs, engine.t.vocab_size
     n = ops.lm_head_search_num_partials(R)
@@ -110,6 +191,12 @@ def _forced_token(cur_len, max_length, forced_bos, forced_eos):
     return f
 
 
+def _step(engine, cache, tokens, pos):
+    if cache.fused is not None:
+        return decode_step_fused(engine, cache, tokens, pos, cache.fused)
+    return decode_step(engine, cache, tokens, pos)
+
+
 def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams, min_length,
                  forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping):
     """Enqueue encode + the whole search loop on the current stream (no host synchronisation inside:
@@ -122,6 +209,8 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
     enc = engine.encode(px, trunc_int=True, save=False, tag="gen.enc")
     enc_kv = engine.cross_kv(enc, tag="gen.enc")
     cache = DecodeCache(engine, R, Lmax, enc_kv, K, use_ancestors=K > 1)
+    if getattr(engine, "fused_decoder", True):
+        cache.fused = fused_prepare(engine, cache)        # plan + this call's packed weights
     ws = _search_ws(engine, R)
     active = torch.ones(1, dtype=I32, device=dev)
     next_token = torch.full((R,), decoder_start_token_id, dtype=I32, device=dev)
@@ -135,7 +224,7 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
             forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
             last = cur_len == Lmax - 1
             if not (last and forced >= 0):
-                hf = decode_step(engine, cache, st["next_token"], cur_len - 1)
+                hf = _step(engine, cache, st["next_token"], cur_len - 1)
             if forced < 0:
                 mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
                 ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mt, ws)
@@ -156,7 +245,7 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
         forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
         last = cur_len == Lmax - 1
         if not (last and forced >= 0):
-            hf = decode_step(engine, cache, st["next_token"], cur_len - 1)
+            hf = _step(engine, cache, st["next_token"], cur_len - 1)
         if forced < 0:
             mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
             ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mt, ws)

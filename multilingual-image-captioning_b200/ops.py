@@ -6,6 +6,8 @@ torch math.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from ._lib import lib, check
@@ -151,6 +153,55 @@ def residual_ln_fwd(acc, bias, x, gamma, beta, eps, out):
     M, d = x.shape
     _call("mic_residual_ln_fwd", _p(acc), _p(bias), _p(x), _p(gamma), _p(beta), float(eps), _p(out), M, d)
     return out
+
+
+_LAYER_FIELDS = ("ln_sa_g", "ln_sa_b", "sa_qkv_w", "sa_qkv_b", "sa_o_w", "sa_o_b", "ln_ca_g", "ln_ca_b", "ca_q_w", "ca_q_b",
+                 "ca_o_w", "ca_o_b", "ln_f_g", "ln_f_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "self_kv", "enc_k", "enc_v")
+_BUFFER_FIELDS = ("x", "q", "a_tiles", "o_tiles", "g_tiles", "acc", "q_acc", "ancestors", "h_out", "ln_out_g", "ln_out_b")
+
+
+class DecoderLayerT(ctypes.Structure):        # mic_decoder_layer_t
+    _fields_ = [(n, ctypes.c_void_p) for n in _LAYER_FIELDS]
+
+
+class DecoderBuffersT(ctypes.Structure):      # mic_decoder_buffers_t
+    _fields_ = [(n, ctypes.c_void_p) for n in _BUFFER_FIELDS]
+
+
+def decoder_plan_bytes(num_layers):
+    return lib().mic_decoder_plan_bytes(num_layers)
+
+
+def decoder_packed_bytes(num_layers, d_model, ffn_dim):
+    return lib().mic_decoder_packed_bytes(num_layers, d_model, ffn_dim)
+
+
+def decoder_layers_struct(layers):
+    """layers: list of dicts field -> tensor -> ctypes array of mic_decoder_layer_t"""
+    arr = (DecoderLayerT * len(layers))()
+    for i, l in enumerate(layers):
+        for n in _LAYER_FIELDS:
+            setattr(arr[i], n, l[n].data_ptr())
+    return arr
+
+
+def decoder_pack_weights(layers_struct, d_model, ffn_dim, packed):
+    _call("mic_decoder_pack_weights", ctypes.cast(layers_struct, ctypes.c_void_p), len(layers_struct), d_model, ffn_dim,
+          _p(packed))
+
+
+def decoder_plan_init(plan, layers_struct, buffers, packed, R, d_model, heads, ffn_dim, cache_len, enc_tokens,
+                      rows_per_image, ld_enc, act, eps):
+    bt = DecoderBuffersT()
+    for n in _BUFFER_FIELDS:
+        setattr(bt, n, _p(buffers[n]))
+    _call("mic_decoder_plan_init", _p(plan), ctypes.cast(layers_struct, ctypes.c_void_p), len(layers_struct),
+          ctypes.cast(ctypes.pointer(bt), ctypes.c_void_p), _p(packed), R, d_model, heads, ffn_dim, cache_len,
+          enc_tokens, rows_per_image, ld_enc, ACT[act], eps)
+
+
+def decoder_step(plan, num_layers, R, pos, sync, phase_times=None):
+    _call("mic_decoder_step", _p(plan), num_layers, R, pos, _p(sync), _p(phase_times))
 
 
 def launch_options(pdl=-1, gemm_b_static=-1):

@@ -1,0 +1,44 @@
+"""Per-phase timing of the persistent decoder-step kernel (globaltimer stamps at every grid-barrier arrival)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import mic_b200
+from mic_b200 import synthetic, generation as gen, ops
+
+cfg = mic_b200.clip_mbart_config()
+model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, seed=0)
+eng = model.engine
+B, K, T = 64, 4, 64
+R = B * K
+px = torch.from_numpy(synthetic.make_batch(cfg, B, 64, seed=7)["pixel_values"]).cuda()
+enc = eng.encode(px, trunc_int=True, save=False, tag="gen.enc")
+enc_kv = eng.cross_kv(enc, tag="gen.enc")
+cache = gen.DecodeCache(eng, R, T, enc_kv, K, use_ancestors=True)
+tokens = torch.randint(4, 250000, (R,), dtype=torch.int32, device="cuda")
+for pos in range(40):                      # fill the cache a bit
+    gen.decode_step_fused(eng, cache, tokens, pos)
+fp = gen.fused_prepare(eng, cache)
+plan, sync = fp['plan'], fp['sync']
+L = cfg.mbart_config.decoder_layers
+G = torch.cuda.get_device_properties(0).multi_processor_count
+P = 1 + 11 * L
+prof = torch.zeros(P * G + 256, dtype=torch.int64, device="cuda")
+pos = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+for _ in range(3):
+    ops.decoder_step(plan, L, R, pos, sync, prof)
+torch.cuda.synchronize()
+raw = prof.cpu().numpy().astype(np.int64)
+t = raw[:P * G].reshape(P, G)
+tr = raw[P * G:]
+end = t.max(axis=1)                        # phase complete = last arrival
+first = t.min(axis=1)
+names = ["qkv", "self_attn", "sa_o", "ln_ca", "ca_q", "cross_attn", "ca_o", "ln_f", "fc1", "fc2", "ln_next"]
+dur = np.diff(end).reshape(L, 11)          # phase 0 (LN_0) is the time origin
+spread = (end - first)[1:].reshape(L, 11)
+print(f"pos={pos}  total step (first arrival of phase 0 -> last of phase {P - 1}): {(end[-1] - first[0]) / 1e3:.1f} us")
+print("phase        mean us   (arrival spread us)")
+for i, n in enumerate(names):
+    print(f"{n:11s} {dur[:, i].mean() / 1e3:8.2f}   {spread[:, i].mean() / 1e3:8.2f}")
+print(f"per layer: {dur.sum(axis=1).mean() / 1e3:.1f} us")
+
