@@ -28,13 +28,12 @@ extern "C" {
 const char* mic_last_error(void);
 int mic_abi_version(void);
 
-/* Launch behaviour of every entry point called afterwards on this thread (-1 = leave unchanged).
+/* Launch behaviour of the HBM-bound (non-GEMM) entry points called afterwards on this thread (-1 = leave unchanged).
  * programmatic_dependent_launch (default 0): kernels are launched with
  *   cudaLaunchAttributeProgrammaticStreamSerialization and call griddepcontrol.wait before touching any buffer,
- *   so their prologue (barrier init, TMEM alloc, descriptor prefetch) overlaps the previous kernel's tail.
- * gemm_b_static (default 0): the caller promises that the B operand (the weight) of the following
- *   mic_gemm_bf16 / mic_lm_head_search calls is not written by any kernel still in flight (decode loop:
- *   frozen parameters), so the first pipeline stages are filled with weight tiles BEFORE that wait. */
+ *   so their prologue overlaps the previous kernel's tail.  Measured on B200 inside CUDA graphs: no gain
+ *   (profiles/r01_pdl_microbench.txt), hence off; the tcgen05 GEMMs never use it.
+ * gemm_b_static: reserved (ignored). */
 int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static);
 
 /* ---- dense contraction ------------------------------------------------------------------------

@@ -420,4 +420,161 @@ __device__ __forceinline__ void decode_attn_group_staged(const DecAttnArgs& a, i
   __syncwarp();     // the stage is refilled by the warp's next item
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the staged item (persistent kernel).  A lone warp per item is instruction-latency bound
+// (~5 cycles per dependent instruction, nothing to overlap with), so the ~2400 scalar instructions of the SIMT
+// version cost more than its memory traffic; here S = Q K^T and O = P V are warp-level m16n8k16 bf16 MMAs fed by
+// ldmatrix straight from the swizzled K / V stage (~250 instructions per item).  The item's <= 4 query rows sit
+// in rows 0..3 of the 16-row MMA tile; rows 8..15 are hard zeros (their A registers), rows 4..7 are zero-filled.
+//   q_stage: bf16 [8][72] (144-byte pitch: conflict-free fragment loads)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int kv_item, int h, uint8_t* kv_smem,
+                                                      bf16* q_stage, int lane) {
+  constexpr int QP = 72;                       // q_stage row pitch in elements
+  const int nk = a.n_keys;
+  const int rpk = a.rows_per_kv;
+  const int r0 = kv_item * rpk;
+  int row0 = kv_item, row1 = kv_item;          // cache rows of keys lane, lane + 32
+  if (a.anc) {
+    row0 = lane < nk ? a.anc[(long long)r0 * a.T + lane] : 0;
+    row1 = lane + 32 < nk ? a.anc[(long long)r0 * a.T + 32 + lane] : 0;
+  }
+  const uint32_t kv_base = smem_u32(kv_smem);
+  const int total = nk * 16;
+  for (int base = 0; base < total; base += 32) {
+    const int idx = base + lane;
+    const int j = idx >> 4, c = idx & 15;
+    const int rj0 = __shfl_sync(0xffffffffu, row0, j & 31), rj1 = __shfl_sync(0xffffffffu, row1, j & 31);
+    if (idx < total) {
+      const int rj = j < 32 ? rj0 : rj1;
+      const int cc = c & 7;
+      const bf16* src = (c < 8 ? a.kc : a.vc) + ((long long)rj * a.T + j) * a.ldkv + h * HD + cc * 8;
+      cp_async_16(kv_base + (c < 8 ? 0 : 8192) + j * 128 + ((cc ^ (j & 7)) << 4), src);
+    }
+  }
+  cp_async_commit();
+  // V rows nk .. next multiple of 16 take part in the P.V MMAs with P = 0: they must be finite
+  {
+    const int pad_rows = ((nk + 15) & ~15) - nk;
+    for (int i = lane; i < pad_rows * 8; i += 32)
+      *reinterpret_cast<uint4*>(kv_smem + 8192 + (nk + (i >> 3)) * 128 + ((i & 7) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  // queries -> bf16 stage rows 0..rpk-1 (pre-scaled: 1/8 is exact), zero rows rpk..7; 64 16-byte chunks, 2 per lane
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int id = lane + t * 32;
+    const int rr = id >> 3, c8 = (id & 7) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (rr < rpk && r0 + rr < a.R) {
+      const int r = r0 + rr;
+      if (a.q != nullptr) {
+        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
+      } else {
+        float* qa = a.q_acc + (long long)r * a.ldq + h * HD + c8;
+        float b[8];
+        load8f_cg(qa, f);
+        load8f(a.q_bias + h * HD + c8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] + b[j]);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(qa) = z;                  // hand the split-K accumulator back zeroed
+        *reinterpret_cast<float4*>(qa + 4) = z;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= a.scale;
+    }
+    store8(q_stage + rr * QP + c8, f);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int npairs = (nk + 15) >> 4;           // 16-key groups
+  // ---- S = Q K^T : rows g (0..7), 16-key groups
+  float sacc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(q_stage + g * QP + ks * 16 + 2 * t4);
+    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(q_stage + g * QP + ks * 16 + 8 + 2 * t4);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      if (np < npairs) {
+        const int key = np * 16 + (lane >> 4) * 8 + (lane & 7);
+        const int chunk = ks * 2 + ((lane >> 3) & 1);
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(kv_base + key * 128 + ((chunk ^ (key & 7)) << 4)));
+        mma_16816(sacc[2 * np], a0, 0u, a2, 0u, b0, b1);
+        mma_16816(sacc[2 * np + 1], a0, 0u, a2, 0u, b2, b3);
+      }
+    }
+  }
+  // ---- softmax over the keys of row g (4 lanes share a row)
+  float mx = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = n * 8 + 2 * t4;
+    if (col >= nk) sacc[n][0] = -INFINITY;
+    if (col + 1 >= nk) sacc[n][1] = -INFINITY;
+    mx = fmaxf(mx, fmaxf(sacc[n][0], sacc[n][1]));
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+  uint32_t pa[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const float p0 = __expf(sacc[n][0] - mx), p1 = __expf(sacc[n][1] - mx);     // exp(-inf) = 0 for masked keys
+    sum += p0 + p1;
+    pa[n] = pack_bf16(p0, p1);
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  const float inv = 1.0f / sum;
+  // ---- O = P V : the S accumulator layout is the A-fragment layout of the next MMA (k = keys)
+  float oacc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+#pragma unroll
+  for (int kp = 0; kp < 4; ++kp) {
+    if (kp < npairs) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        const int mi = lane >> 3;
+        const int key = kp * 16 + (mi & 1) * 8 + (lane & 7);
+        const int chunk = dp * 2 + (mi >> 1);
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(kv_base + 8192 + key * 128 + ((chunk ^ (key & 7)) << 4)));
+        mma_16816(oacc[2 * dp], pa[2 * kp], 0u, pa[2 * kp + 1], 0u, b0, b1);
+        mma_16816(oacc[2 * dp + 1], pa[2 * kp], 0u, pa[2 * kp + 1], 0u, b2, b3);
+      }
+    }
+  }
+  if (g < rpk && r0 + g < a.R) {
+    const int r = r0 + g;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      bf16* dst = a.o + (a.o_tiled_kb ? tiled_off(r, h * HD + n * 8, a.o_tiled_kb) : (long long)r * a.ldo + h * HD + n * 8) +
+                  2 * t4;
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16(oacc[n][0] * inv, oacc[n][1] * inv);
+    }
+  }
+  __syncwarp();     // the stages are refilled by the warp's next item
+}
+
 }  // namespace micdec

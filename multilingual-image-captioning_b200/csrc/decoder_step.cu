@@ -37,7 +37,9 @@ constexpr int STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BK * BN * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EW = 8;                         // epilogue / vector warps
 constexpr int THREADS = 128 + EW * 32;
-constexpr int TMEM_COLS = 128;                // two 64-column fp32 accumulators
+constexpr int NACC = 1;                       // (4 independent accumulators per unit were tried: no gain, the MMA
+                                              // chain is not what bounds a unit - the L2 -> SM operand stream is)
+constexpr int TMEM_COLS = 2 * NACC * BN;      // double-buffered
 constexpr int VEC_SCRATCH = EW * 2048;        // per-warp attention scratch: queries [4, 64] f32, numerators [64], spare
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + VEC_SCRATCH + 256 + 1024;
 
@@ -107,6 +109,8 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 
+constexpr int TRACE_PHASE = 1 + 8 + 11 * 5, TRACE_CTA = 1;   // fine trace (prof != null): fc1 of layer 5 on one CTA
+
 __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
             if (round > 0) mbar_wait(&empty_bar[slot], (round - 1) & 1);
             mbar_arrive_expect_tx(&full_bar[slot], STAGE_BYTES);
             bulk_load(smem_b + slot * B_BYTES, t.b_src + (long long)kb * (B_BYTES / 2), B_BYTES, &full_bar[slot]);
+            if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE) args.prof[(long long)P * G + 32 + i] = gtime();
             if (++kb == kb_end) kb = t.kb_lo;
             if (++slot == STAGES) {
               slot = 0;
@@ -185,6 +190,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           fence_acquire_gpu();
           fence_proxy_async_global();
         }
+        const bool trc = args.prof && cta == TRACE_CTA && p == TRACE_PHASE;
+        if (trc) args.prof[(long long)P * G + 129] = gtime();
         for (int u = cta; u < units; u += G) {
           const Unit t = unit_of(ph, u, m_tiles);
           int kb = t.kb_lo + t.rot;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           for (int i = 0; i < t.len; ++i) {
             if (round > 0) mbar_wait(&empty_bar[slot], (round - 1) & 1);
             bulk_load(smem_a + slot * A_BYTES, t.a_src + (long long)kb * (A_BYTES / 2), A_BYTES, &full_bar[slot]);
+            if (trc) args.prof[(long long)P * G + i] = gtime();
             if (++kb == kb_end) kb = t.kb_lo;
             if (++slot == STAGES) {
               slot = 0;
@@ -223,11 +231,12 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           const uint32_t as = it & 1, aphase = (it >> 1) & 1;
           mbar_wait(&tmem_empty[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + as * BN;
+          const uint32_t tmem_d = tmem_base + as * (NACC * BN);
 #pragma unroll 1
           for (int i = 0; i < len; ++i) {
             mbar_wait(&full_bar[slot], fpar);
             tcgen05_fence_after();
+            if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE) args.prof[(long long)P * G + 64 + i] = gtime();
             const uint64_t da = da0 + (uint64_t)((slot * A_BYTES) >> 4);
             const uint64_t db = db0 + (uint64_t)((slot * B_BYTES) >> 4);
 #pragma unroll
@@ -253,7 +262,6 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
     // on this phase's barrier; only its weight tiles are prefetched, into the B half) -> 16 KB K/V stage per warp
     uint8_t* kv_stage = smem_a + ew * A_BYTES * (STAGES / EW);
     float* q_smem = reinterpret_cast<float*>(vec + ew * 2048);
-    float* p_smem = q_smem + 4 * HD;
     float* ln_part = reinterpret_cast<float*>(vec + EW * 2048 - 256);      // [2 parities][8 warps][2] LayerNorm partials
     const int vt = threadIdx.x - 128;          // 0..255 among the vector warps
     const bool leader = threadIdx.x == 128;
@@ -273,45 +281,51 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         for (int u = cta; u < units; u += G, ++it) {
           const int m = u % m_tiles, n = (u / m_tiles) % ph.n_tiles;
           const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-          mbar_wait(&tmem_full[as], aphase);
-          tcgen05_fence_after();
           const int row = m * BM + quarter * 32 + lane;
           const int col0 = n * BN + half * 32;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * 32;
+          float bias_r[32];                            // fetched while the MMAs are still running
+          if (ph.kind == PH_GEMM_STORE) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) load8f(ph.bias + col0 + j, bias_r + j);
+          }
+          mbar_wait(&tmem_full[as], aphase);
+          tcgen05_fence_after();
+          if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 128] = gtime();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * (NACC * BN) + half * 32;
           const bool to_cache = col0 >= ph.col_split;
           bf16* dst = to_cache ? ph.out2 + (long long)row * ph.ldo2 + (long long)args.pos * ph.pos_pitch +
                                      (col0 - ph.col_split)
                                : reinterpret_cast<bf16*>(ph.out) + (long long)row * ph.ldo + col0;
           float* racc = reinterpret_cast<float*>(ph.out) + (long long)row * ph.ldo + col0;
-          // 8 columns at a time, rolled (code size)
-#pragma unroll 1
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
-            tmem_ld_32x32_x8(taddr + j, v);
-            tmem_ld_wait();
-            if (j == 24) {                             // accumulator drained: hand the TMEM buffer back
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[as]);
-            }
-            if (row < args.R) {
-              if (ph.kind == PH_GEMM_RED) {
-                red_add_v4_f32(racc + j, v[0], v[1], v[2], v[3]);
-                red_add_v4_f32(racc + j + 4, v[4], v[5], v[6], v[7]);
-              } else {
-                float b[8];
-                load8f(ph.bias + col0 + j, b);
+          float v[32];
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);      // accumulator drained: hand the TMEM buffer back
+          if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 132] = gtime();
+          if (row < args.R) {
+            if (ph.kind == PH_GEMM_RED) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_v4_f32(racc + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              // fully unrolled on purpose: four independent 8-column chains give the lone warp some ILP
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
                 if (ph.act == MIC_ACT_GELU) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = act_fwd(v[e] + b[e], MIC_ACT_GELU);
+                  for (int e = 0; e < 8; ++e) v[j + e] = act_fwd(v[j + e] + bias_r[j + e], MIC_ACT_GELU);
                 } else {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] += b[e];
+                  for (int e = 0; e < 8; ++e) v[j + e] += bias_r[j + e];
+                }
+                if (j == 24 && args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) {
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(args.prof[(long long)P * G + 133]) : "f"(v[31]), "f"(v[0]), "f"(v[8]), "f"(v[16]));
                 }
                 if (!to_cache && ph.out_tiled_kb)
-                  store8(reinterpret_cast<bf16*>(ph.out) + tiled_off(row, col0 + j, ph.out_tiled_kb), v);
+                  store8(reinterpret_cast<bf16*>(ph.out) + tiled_off(row, col0 + j, ph.out_tiled_kb), v + j);
                 else
-                  store8(dst + j, v);
+                  store8(dst + j, v + j);
               }
             }
           }
@@ -382,12 +396,14 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           const int items = ((a.R + a.rows_per_kv - 1) / a.rows_per_kv) * a.H;
 #pragma unroll 1
           for (int i = gw; i < items; i += nw)
-            decode_attn_group_staged(a, i / a.H, i % a.H, kv_stage, q_smem, p_smem, lane);
+            decode_attn_group_mma(a, i / a.H, i % a.H, kv_stage, reinterpret_cast<bf16*>(q_smem), lane);
         }
       }
       // generic-proxy writes of this phase (tile-image activations in global memory, ring scratch in shared memory)
       // are ordered before the async-proxy bulk copies that follow the barrier
+      if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 130] = gtime();
       fence_proxy_async_global();
+      if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 131] = gtime();
       // ---- grid barrier arrival: this CTA's writes of phase p are done.  The leader's release (gpu scope) is
       // cumulative over the other warps' writes, which precede it through the CTA barrier.
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");

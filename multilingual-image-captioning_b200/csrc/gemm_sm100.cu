@@ -139,7 +139,6 @@ static int setup_operands(Operands* o, int a_mn, int b_mn, const void* A, long l
   if (s.group_m < 1) s.group_m = 1;
   s.split_k = 1;
   s.kb_per_split = (K + BLOCK_K - 1) / BLOCK_K;
-  s.prefetch_b = 0;
   return MIC_OK;
 }
 
@@ -153,8 +152,10 @@ static int launch_one(cudaStream_t stream, const Operands& o, const typename Epi
   }
   const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks * o.shape.split_k;
   const int grid = tiles < mic_num_sms() ? tiles : mic_num_sms();
-  MIC_CHECK_CUDA(mic_launch(kern, dim3(grid), dim3(Cfg<BN, Epi::NBUF, Epi::EW>::THREADS),
-                            Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES, stream, o.ta, o.tb, o.td, o.td2, o.shape, ep));
+  // (plain launch: the tcgen05 GEMM does not take part in programmatic dependent launch - its producer loop is
+  //  kept minimal; a PDL-aware variant with weight prefetch cost the training step 7 %)
+  kern<<<grid, Cfg<BN, Epi::NBUF, Epi::EW>::THREADS, Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.td, o.td2, o.shape, ep);
+  MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
 
@@ -233,7 +234,6 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
       }
     }
   }
-  o.shape.prefetch_b = g_mic_launch.static_b;
   if (split_k > 1) {
     MIC_CHECK_ARG(can_split, "split_k needs a plain fp32 TMA-storable output (no bias/act/residual)");
     o.shape.kb_per_split = (nkb + split_k - 1) / split_k;
@@ -311,8 +311,8 @@ extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, co
     MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
     attr_set = true;
   }
-  o.shape.prefetch_b = g_mic_launch.static_b;
-  MIC_CHECK_CUDA(mic_launch(kern, dim3(search_grid(M)), dim3(NUM_THREADS), Cfg<256>::SMEM_BYTES,
-                            reinterpret_cast<cudaStream_t>(stream), o.ta, o.tb, o.td, o.td2, o.shape, ep));
+  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
+      o.ta, o.tb, o.td, o.td2, o.shape, ep);
+  MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

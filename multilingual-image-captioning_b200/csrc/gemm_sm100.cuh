@@ -53,7 +53,6 @@ struct Shape {
   int num_m_blocks, num_n_blocks, group_m;
   int split_k;        // >1: K is cut into `split_k` slices, one work unit each, combined by TMA reduce-add
   int kb_per_split;   // k-blocks per slice
-  int prefetch_b;     // B is static (weights): the producer fills its first stages with B tiles before pdl_wait
 };
 
 struct TileCoord {
@@ -619,34 +618,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_trigger();                                  // this CTA holds its smem/TMEM: the next kernel may be scheduled
-  if (threadIdx.x != 0) pdl_wait();               // (the producer thread waits after its static-operand prefetch)
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      auto load_b = [&](int stage, int k0, int n0) {
-        uint8_t* sb = smem_b + stage * C::B_BYTES;
-        if (B_MN == 0) {
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
-        } else {
-#pragma unroll
-          for (int i = 0; i < BN / 64; ++i)
-            tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
-        }
-      };
-      int armed = 0;                               // leading stages whose barrier is armed and B tile in flight
-      if (shape.prefetch_b && (int)blockIdx.x < num_units) {
-        const int u = blockIdx.x;
-        const TileCoord tc = tile_coord(shape, u % num_tiles);
-        const int kb0 = (u / num_tiles) * shape.kb_per_split;
-        const int kb1 = min(kb0 + shape.kb_per_split, num_k_blocks);
-        for (int kb = kb0; kb < kb1 && armed < C::STAGES; ++kb, ++armed) {
-          mbar_arrive_expect_tx(&full_bar[armed], C::STAGE_BYTES);
-          load_b(armed, kb * BLOCK_K, tc.n_blk * BN);
-        }
-      }
-      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -655,21 +630,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int kb0 = (u / num_tiles) * shape.kb_per_split;
         const int kb1 = min(kb0 + shape.kb_per_split, num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int k0 = kb * BLOCK_K;
-          if (armed > 0) {
-            --armed;
-          } else {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            load_b(stage, k0, n0);
-          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_BYTES;
+          const int k0 = kb * BLOCK_K;
           if (A_MN == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)
               tma_load_2d(sa + i * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + i * 64, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
           }
           if (++stage == C::STAGES) {
             stage = 0;

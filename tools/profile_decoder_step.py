@@ -42,3 +42,13 @@ for i, n in enumerate(names):
     print(f"{n:11s} {dur[:, i].mean() / 1e3:8.2f}   {spread[:, i].mean() / 1e3:8.2f}")
 print(f"per layer: {dur.sum(axis=1).mean() / 1e3:.1f} us")
 
+TP = 1 + 8 + 11 * 5
+t0 = end[TP - 1]
+f = lambda xs: " ".join(f"{(x - t0) / 1e3:.2f}" for x in xs)
+print(f"fine trace of fc1/layer5 on CTA 1 (us after the previous phase completed; CTA's own arrival {(t[TP, 1] - t0) / 1e3:.2f}):")
+print("  dependency seen by the activation producer:", f(tr[129:130]))
+print("  W issue :", f(tr[32:48]))
+print("  A issue :", f(tr[0:16]))
+print("  full bar:", f(tr[64:80]))
+print("  epilogue: accumulator ready", f(tr[128:129]), " stores issued", f(tr[130:131]), " proxy fence done", f(tr[131:132]))
+print("  epilogue detail: tmem loaded", f(tr[132:133]), " gelu done", f(tr[133:134]))
