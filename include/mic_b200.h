@@ -85,6 +85,16 @@ int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E
                        const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
                        float* cand_val, int* cand_idx);
 
+/* packed-operand variant of mic_lm_head_search: H and E are given as K-major tile images (mic_pack_kmajor_tiles:
+ * H with tile_rows = 128 - the persistent decoder step writes it directly -, E with tile_rows = 256), so that a
+ * pipeline stage is two contiguous bulk copies instead of 384 TMA box rows (the TMA unit's row rate bounds the
+ * unpacked kernel at ~2.5 TB/s of the 512 MB table).  Same outputs as mic_lm_head_search. */
+long long mic_pack_kmajor_tiles_bytes(long long rows, int K, int tile_rows);
+int mic_pack_kmajor_tiles(void* stream, const void* src, long long ld, long long rows, int K, int tile_rows, void* out);
+int mic_lm_head_search_packed(void* stream, const void* h_tiles, const void* e_tiles, const float* bias,
+                              int mask_token, int M, int V, int K, float* pmax, float* psum, float* cand_val,
+                              int* cand_idx);
+
 /* ---- normalisation / embedding / elementwise (HBM-bound, vectorised, warp-shuffle reductions) ----
  * flax.linen.LayerNorm (fp32 statistics, var = E[x^2]-E[x]^2) as used by FlaxCLIPEncoderLayer,
  * pre_layrnorm, FlaxMBartDecoderLayer, layernorm_embedding, layer_norm [E2,E5,D5,D6]. x,y bf16 [M,d]. */
@@ -186,6 +196,8 @@ typedef struct {
   const int* ancestors;                            /* [R, cache_len] beam ancestor table or NULL */
   void* h_out;                                     /* bf16 [R, d] row-major result              */
   const float* ln_out_g; const float* ln_out_b;    /* decoder layer_norm                        */
+  void* h_out_tiles;                               /* optional: result as a 128-row tile image instead (input of
+                                                      mic_lm_head_search_packed); h_out is then not written */
 } mic_decoder_buffers_t;
 long long mic_decoder_plan_bytes(int num_layers);
 long long mic_decoder_packed_bytes(int num_layers, int d_model, int ffn_dim);

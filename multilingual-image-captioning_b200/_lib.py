@@ -33,6 +33,9 @@ SIGNATURES = {
     "mic_lm_head_ce_grad": [P, P, L, P, L, P, P, P, P, F, F, I, I, I, P, L],
     "mic_lm_head_search_num_partials": [I],
     "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P],
+    "mic_pack_kmajor_tiles_bytes": [L, I, I],
+    "mic_pack_kmajor_tiles": [P, P, L, L, I, I, P],
+    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P],
     "mic_layernorm_fwd": [P, P, P, P, F, P, P, P, I, I],
     "mic_residual_ln_fwd": [P, P, P, P, P, P, F, P, I, I],
     "mic_layernorm_bwd_workspace_floats": [I, I],
@@ -90,7 +93,7 @@ def lib() -> C.CDLL:
     for name, args in SIGNATURES.items():
         fn = getattr(l, name)       # AttributeError if the symbol is not exported -> loud
         fn.argtypes = args
-        fn.restype = L if name.endswith(("_workspace_floats", "_plan_bytes", "_packed_bytes")) else I
+        fn.restype = L if name.endswith(("_workspace_floats", "_plan_bytes", "_packed_bytes", "_tiles_bytes")) else I
     l.mic_last_error.argtypes = []
     l.mic_last_error.restype = C.c_char_p
     if l.mic_abi_version() != 1:

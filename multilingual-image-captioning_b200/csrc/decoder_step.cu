@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         const int units = m_tiles * ph.n_tiles * ph.split_k;
         if (cta >= units) continue;
         if (p > 0) {
-          while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(64);
+          while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
           fence_acquire_gpu();
           fence_proxy_async_global();
         }
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           // no work here: still do not arrive for phase p before phase p-1 is complete everywhere, so that
           // (arrivals / G) counts whole phases (CTAs with work inherit this from their gated activation loads)
           if (leader) {
-            while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(64);
+            while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
             fence_acquire_gpu();
           }
         }
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         // vector phase: inputs come from earlier phases of other CTAs
         if (p > 0) {
           if (leader) {
-            while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(64);
+            while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
             fence_acquire_gpu();
           }
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
@@ -402,7 +402,9 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       // generic-proxy writes of this phase (tile-image activations in global memory, ring scratch in shared memory)
       // are ordered before the async-proxy bulk copies that follow the barrier
       if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 130] = gtime();
-      fence_proxy_async_global();
+      // only phases whose output is fetched by bulk copies (tile-image activations) or that used the ring as scratch
+      // need the generic -> async proxy fence (0.6 us); split-K reductions and the q|k|v store feed generic loads
+      if (ph.kind == PH_LN || ph.kind == PH_ATTN || (ph.kind == PH_GEMM_STORE && ph.out_tiled_kb)) fence_proxy_async_global();
       if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 131] = gtime();
       // ---- grid barrier arrival: this CTA's writes of phase p are done.  The leader's release (gpu scope) is
       // cumulative over the other warps' writes, which precede it through the CTA barrier.
@@ -591,7 +593,8 @@ extern "C" int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_dec
     if (l + 1 < L)
       ln(p[10], buf->acc, w.fc2_b, layers[l + 1].ln_sa_g, layers[l + 1].ln_sa_b, buf->a_tiles, d / BK);
     else
-      ln(p[10], buf->acc, w.fc2_b, buf->ln_out_g, buf->ln_out_b, buf->h_out, 0);      // decoder layer_norm, row-major
+      ln(p[10], buf->acc, w.fc2_b, buf->ln_out_g, buf->ln_out_b, buf->h_out_tiles ? buf->h_out_tiles : buf->h_out,
+         buf->h_out_tiles ? d / BK : 0);                                                // decoder layer_norm
   }
   MIC_CHECK_CUDA(cudaMemcpyAsync(plan_dev, host, total, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
   return MIC_OK;

@@ -303,9 +303,80 @@ extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, co
   Operands o;
   int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, mb);
   if (rc) return rc;
-  EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx};
+  EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, nullptr, nullptr};
   // fixed m-block per CTA: grid is a multiple of num_m_blocks and tiles are rasterised m-fastest
   auto kern = gemm_kernel<0, 0, 256, EpiSearch>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
+      o.ta, o.tb, o.td, o.td2, o.shape, ep);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+// ---- packed-operand lm_head search: K-major tile images + bulk copies ---------------------------------------
+namespace {
+// src [rows, K] row-major (pitch ld) -> tiles [row tile][k block] of tile_rows x 64 elements, each the SWIZZLE_128B
+// image of a K-major tcgen05 operand (row r at r*128 B, 16-byte chunk c at c ^ (r & 7)); rows >= `rows` are zeros
+__global__ void __launch_bounds__(256) pack_kmajor_tiles_kernel(const bf16* __restrict__ src, long long ld, int rows,
+                                                                int num_kb, int tile_rows, bf16* __restrict__ out,
+                                                                long long num_tiles) {
+  for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const long long rt = t / num_kb;
+    const int kb = (int)(t % num_kb);
+    bf16* dst = out + t * tile_rows * 64;
+    for (int i = threadIdx.x; i < tile_rows * 8; i += 256) {
+      const int r = i >> 3, c = i & 7;
+      const long long row = rt * tile_rows + r;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row < rows) v = *reinterpret_cast<const uint4*>(src + row * ld + kb * 64 + c * 8);
+      *reinterpret_cast<uint4*>(dst + r * 64 + ((c ^ (r & 7)) << 3)) = v;
+    }
+  }
+}
+}  // namespace
+
+extern "C" long long mic_pack_kmajor_tiles_bytes(long long rows, int K, int tile_rows) {
+  return ((rows + tile_rows - 1) / tile_rows) * tile_rows * (long long)K * 2;
+}
+extern "C" int mic_pack_kmajor_tiles(void* stream, const void* src, long long ld, long long rows, int K, int tile_rows,
+                                     void* out) {
+  MIC_CHECK_ARG(src && out && K % 64 == 0 && (tile_rows == 128 || tile_rows == 256) && rows > 0 && ld % 8 == 0,
+                "pack_kmajor_tiles: K=%d must be a multiple of 64, tile_rows %d in {128, 256}", K, tile_rows);
+  MIC_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 1023) == 0, "pack_kmajor_tiles: output must be 1024-byte aligned");
+  const long long tiles = ((rows + tile_rows - 1) / tile_rows) * (K / 64);
+  const int grid = (int)(tiles < 148ll * 16 ? tiles : 148ll * 16);
+  pack_kmajor_tiles_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)src, ld, (int)rows, K / 64, tile_rows, (bf16*)out, tiles);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_lm_head_search_packed(void* stream, const void* h_tiles, const void* e_tiles, const float* bias,
+                                         int mask_token, int M, int V, int K, float* pmax, float* psum,
+                                         float* cand_val, int* cand_idx) {
+  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  MIC_CHECK_ARG(mb <= mic_num_sms(), "lm_head_search: M=%d rows exceed one m-block per SM", M);
+  MIC_CHECK_ARG(K % 64 == 0 && h_tiles && e_tiles, "lm_head_search_packed: K=%d must be a multiple of 64", K);
+  MIC_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_tiles) | reinterpret_cast<uintptr_t>(e_tiles)) & 1023) == 0,
+                "lm_head_search_packed: tile buffers must be 1024-byte aligned");
+  Operands o;
+  memset(&o, 0, sizeof(o));
+  o.bn = 256;
+  Shape& s = o.shape;
+  s.M = M;
+  s.N = V;
+  s.K = K;
+  s.num_m_blocks = mb;
+  s.num_n_blocks = (V + 255) / 256;
+  s.group_m = mb;
+  s.split_k = 1;
+  s.kb_per_split = K / BLOCK_K;
+  EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, (const bf16*)h_tiles, (const bf16*)e_tiles};
+  auto kern = gemm_kernel<0, 0, 256, EpiSearchPacked>;
   static bool attr_set = false;
   if (!attr_set) {
     MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));

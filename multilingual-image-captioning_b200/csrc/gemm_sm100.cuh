@@ -474,6 +474,10 @@ struct EpiSearchParams {
   float* psum;         // [num_partials, M]
   float* cand_val;     // [num_partials, M, SEARCH_TOPK] raw logits (descending)
   int* cand_idx;       // [num_partials, M, SEARCH_TOPK] vocab ids
+  // packed-operand variant (EpiSearchPacked): both operands pre-arranged as contiguous SWIZZLE_128B tile images
+  // [row tile][k block], fetched with one bulk copy per operand per stage instead of 384 TMA box rows
+  const bf16* a_tiles;
+  const bf16* b_tiles;
 };
 
 // The launcher sizes the grid as a multiple of num_m_blocks with group_m == num_m_blocks, so every CTA
@@ -570,6 +574,10 @@ struct EpiSearch {
   }
 };
 
+struct EpiSearchPacked : EpiSearch {};
+template <class Epi> struct PackedOperands { static constexpr bool value = false; };
+template <> struct PackedOperands<EpiSearchPacked> { static constexpr bool value = true; };
+
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
@@ -598,7 +606,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int num_units = num_tiles * shape.split_k;
   const int num_k_blocks = (shape.K + BLOCK_K - 1) / BLOCK_K;
 
-  if (warp == 0 && lane == 0) {
+  if (!PackedOperands<Epi>::value && warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
   }
@@ -635,14 +643,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint8_t* sa = smem_a + stage * C::A_BYTES;
           uint8_t* sb = smem_b + stage * C::B_BYTES;
           const int k0 = kb * BLOCK_K;
-          if (A_MN == 0) {
+          if constexpr (PackedOperands<Epi>::value) {
+            bulk_load(sa, ep.a_tiles + ((long long)tc.m_blk * num_k_blocks + kb) * (C::A_BYTES / 2), C::A_BYTES,
+                      &full_bar[stage]);
+            bulk_load(sb, ep.b_tiles + ((long long)tc.n_blk * num_k_blocks + kb) * (C::B_BYTES / 2), C::B_BYTES,
+                      &full_bar[stage]);
+          } else if (A_MN == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)
               tma_load_2d(sa + i * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + i * 64, k0);
           }
-          if (B_MN == 0) {
+          if constexpr (PackedOperands<Epi>::value) {
+          } else if (B_MN == 0) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
           } else {
 #pragma unroll

@@ -100,8 +100,9 @@ def _aligned(engine, name, nbytes, align=1024):
     return raw[off:off + nbytes]
 
 
-def _fused_plan(engine, cache: DecodeCache):
-    """Phase table of the persistent decoder-step kernel for this buffer set (built once per buffer set)."""
+def _fused_plan(engine, cache: DecodeCache, tiled_out=False):
+    """Phase table of the persistent decoder-step kernel for this buffer set (built once per buffer set).
+    tiled_out: the final hidden states are written as a tile image for the packed lm_head search."""
     t, ps, b = engine.t, engine.ps, engine.bufs
     R, d, T, L = cache.rows, t.d_model, cache.T, t.decoder_layers
     F = t.decoder_ffn_dim
@@ -109,7 +110,8 @@ def _fused_plan(engine, cache: DecodeCache):
     bufs = {"x": b.get("gen.x", (R, d)), "q": b.get("gen.q", (R, d)), "h_out": b.get("gen.a", (R, d)),
             "a_tiles": _aligned(engine, "gen.a_tiles", Rp * d * 2), "o_tiles": _aligned(engine, "gen.o_tiles", Rp * d * 2),
             "g_tiles": _aligned(engine, "gen.g_tiles", Rp * F * 2), "ancestors": cache.ancestors,
-            "ln_out_g": ps.f("d.ln_final.scale"), "ln_out_b": ps.f("d.ln_final.bias")}
+            "ln_out_g": ps.f("d.ln_final.scale"), "ln_out_b": ps.f("d.ln_final.bias"),
+            "h_out_tiles": _aligned(engine, "gen.h_tiles", Rp * d * 2) if tiled_out else None}
     for n in ("acc", "q_acc"):
         z = b.t.get("gen." + n)
         if z is None or tuple(z.shape) != (R, d):
@@ -117,7 +119,7 @@ def _fused_plan(engine, cache: DecodeCache):
             b.t["gen." + n] = z
         bufs[n] = z
     packed = _aligned(engine, "gen.wpack", ops.decoder_packed_bytes(L, d, F))
-    key = (R, T, cache.rows_per_image, cache.enc_kv.data_ptr(), cache.self_kv.data_ptr(), ps.shadow.data_ptr(),
+    key = (R, T, tiled_out, cache.rows_per_image, cache.enc_kv.data_ptr(), cache.self_kv.data_ptr(), ps.shadow.data_ptr(),
            ps.master.data_ptr(), packed.data_ptr()) + tuple(0 if v is None else v.data_ptr() for v in bufs.values())
     plans = engine.__dict__.setdefault("_fused_plans", {})
     entry = plans.get("decoder")
@@ -143,8 +145,9 @@ def _fused_plan(engine, cache: DecodeCache):
     plan = torch.empty(ops.decoder_plan_bytes(L) + 128, dtype=torch.uint8, device=engine.dev)
     plan = plan[(-plan.data_ptr()) % 128:]
     sync = torch.zeros(1, dtype=I32, device=engine.dev)
-    for n in ("a_tiles", "o_tiles", "g_tiles"):
-        bufs[n].zero_()                                   # rows beyond R of the last row tile stay finite
+    for n in ("a_tiles", "o_tiles", "g_tiles", "h_out_tiles"):
+        if bufs[n] is not None:
+            bufs[n].zero_()                                   # rows beyond R of the last row tile stay finite
     ops.decoder_plan_init(plan, lstruct, bufs, packed, R, d, t.decoder_attention_heads, F, T, engine.c.num_tokens,
                           cache.rows_per_image, L * 2 * d, t.activation_function, t.layer_norm_eps)
     fp = {"plan": plan, "sync": sync, "bufs": bufs, "layers": lstruct, "packed": packed}
@@ -152,11 +155,16 @@ def _fused_plan(engine, cache: DecodeCache):
     return fp
 
 
-def fused_prepare(engine, cache: DecodeCache):
-    """Once per generate() call: (re)build the plan if the buffers moved and re-pack the current weights."""
+def fused_prepare(engine, cache: DecodeCache, packed_search=False):
+    """Once per generate() call: (re)build the plan if the buffers moved and re-pack the current weights
+    (and, for the packed lm_head search, the tied embedding table as 256-row tile images)."""
     t = engine.t
-    fp = _fused_plan(engine, cache)
+    fp = _fused_plan(engine, cache, tiled_out=packed_search)
     ops.decoder_pack_weights(fp["layers"], t.d_model, t.decoder_ffn_dim, fp["packed"])
+    if packed_search:
+        emb = engine.ps.w("shared")
+        fp["e_tiles"] = _aligned(engine, "gen.e_tiles", ops.pack_kmajor_tiles_bytes(emb.shape[0], emb.shape[1], 256))
+        ops.pack_kmajor_tiles(emb, 256, fp["e_tiles"])
     return fp
 
 
@@ -169,7 +177,7 @@ def decode_step_fused(engine, cache: DecodeCache, tokens, pos: int, fp=None):
     ops.embed_ln_fwd(tokens, None, 1, pos + t.position_offset, ps.w("shared"), ps.w("d.pos"), engine.emb_scale,
                      ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), t.layer_norm_eps, None, fp["bufs"]["x"])
     ops.decoder_step(fp["plan"], t.decoder_layers, cache.rows, pos, fp["sync"])
-    return fp["bufs"]["h_out"]
+    return fp["bufs"]["h_out_tiles"] if fp["bufs"]["h_out_tiles"] is not None else fp["bufs"]["h_out"]
 
 
 def _search_ws(engine, R):
@@ -197,6 +205,15 @@ def _step(engine, cache, tokens, pos):
     return decode_step(engine, cache, tokens, pos)
 
 
+def _lm_head_search(engine, cache, hf, mask_token, ws):
+    ps, t = engine.ps, engine.t
+    if cache.fused is not None and "e_tiles" in cache.fused:
+        ops.lm_head_search_packed(hf, cache.fused["e_tiles"], ps.f("flb"), int(mask_token), cache.rows, t.vocab_size,
+                                  t.d_model, ws)
+    else:
+        ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws)
+
+
 def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams, min_length,
                  forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping):
     """Enqueue encode + the whole search loop on the current stream (no host synchronisation inside:
@@ -210,7 +227,7 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
     enc_kv = engine.cross_kv(enc, tag="gen.enc")
     cache = DecodeCache(engine, R, Lmax, enc_kv, K, use_ancestors=K > 1)
     if getattr(engine, "fused_decoder", True):
-        cache.fused = fused_prepare(engine, cache)        # plan + this call's packed weights
+        cache.fused = fused_prepare(engine, cache, packed_search=True)     # plan + this call's packed weights
     ws = _search_ws(engine, R)
     active = torch.ones(1, dtype=I32, device=dev)
     next_token = torch.full((R,), decoder_start_token_id, dtype=I32, device=dev)
@@ -227,7 +244,7 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
                 hf = _step(engine, cache, st["next_token"], cur_len - 1)
             if forced < 0:
                 mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
-                ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mt, ws)
+                _lm_head_search(engine, cache, hf, mt, ws)
                 ops.search_merge(ws, R)
             ops.greedy_step(ws, st, forced, R, Lmax, cur_len, eos_token_id, pad_token_id)
             ops.greedy_cond(st, R, cur_len + 1, Lmax)
@@ -248,7 +265,7 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
             hf = _step(engine, cache, st["next_token"], cur_len - 1)
         if forced < 0:
             mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
-            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mt, ws)
+            _lm_head_search(engine, cache, hf, mt, ws)
             ops.search_merge(ws, R)
         ops.beam_step(ws, st, forced, B, K, Lmax, V, cur_len, eos_token_id, early_stopping, length_penalty)
         ops.beam_cond(st, B, K, cur_len + 1, Lmax, length_penalty, early_stopping)

@@ -95,6 +95,20 @@ def lm_head_search_num_partials(M):
     return lib().mic_lm_head_search_num_partials(M)
 
 
+def pack_kmajor_tiles_bytes(rows, K, tile_rows):
+    return lib().mic_pack_kmajor_tiles_bytes(rows, K, tile_rows)
+
+
+def pack_kmajor_tiles(src, tile_rows, out):
+    rows, K = src.shape
+    _call("mic_pack_kmajor_tiles", _p(src), _ld(src), rows, K, tile_rows, _p(out))
+
+
+def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws):
+    _call("mic_lm_head_search_packed", _p(h_tiles), _p(e_tiles), _p(bias), mask_token, M, V, K, _p(ws["pmax"]),
+          _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]))
+
+
 def lm_head_ce_stats(h, emb, bias, labels, ws, logits_out=None):
     M, K = h.shape
     V = emb.shape[0]
@@ -157,7 +171,8 @@ def residual_ln_fwd(acc, bias, x, gamma, beta, eps, out):
 
 _LAYER_FIELDS = ("ln_sa_g", "ln_sa_b", "sa_qkv_w", "sa_qkv_b", "sa_o_w", "sa_o_b", "ln_ca_g", "ln_ca_b", "ca_q_w", "ca_q_b",
                  "ca_o_w", "ca_o_b", "ln_f_g", "ln_f_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "self_kv", "enc_k", "enc_v")
-_BUFFER_FIELDS = ("x", "q", "a_tiles", "o_tiles", "g_tiles", "acc", "q_acc", "ancestors", "h_out", "ln_out_g", "ln_out_b")
+_BUFFER_FIELDS = ("x", "q", "a_tiles", "o_tiles", "g_tiles", "acc", "q_acc", "ancestors", "h_out", "ln_out_g", "ln_out_b",
+                  "h_out_tiles")
 
 
 class DecoderLayerT(ctypes.Structure):        # mic_decoder_layer_t
