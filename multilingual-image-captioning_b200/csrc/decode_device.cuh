@@ -436,71 +436,17 @@ __device__ __forceinline__ void mma_16816(float* d, uint32_t a0, uint32_t a1, ui
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int kv_item, int h, uint8_t* kv_smem,
-                                                      bf16* q_stage, int lane) {
-  constexpr int QP = 72;                       // q_stage row pitch in elements
-  const int nk = a.n_keys;
-  const int rpk = a.rows_per_kv;
-  const int r0 = kv_item * rpk;
-  int row0 = kv_item, row1 = kv_item;          // cache rows of keys lane, lane + 32
-  if (a.anc) {
-    row0 = lane < nk ? a.anc[(long long)r0 * a.T + lane] : 0;
-    row1 = lane + 32 < nk ? a.anc[(long long)r0 * a.T + 32 + lane] : 0;
+#define MIC_TRACE(slot, dep)                                                                          \
+  if (trace) {                                                                                        \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[slot]) : "r"(dep));                         \
   }
-  const uint32_t kv_base = smem_u32(kv_smem);
-  const int total = nk * 16;
-  for (int base = 0; base < total; base += 32) {
-    const int idx = base + lane;
-    const int j = idx >> 4, c = idx & 15;
-    const int rj0 = __shfl_sync(0xffffffffu, row0, j & 31), rj1 = __shfl_sync(0xffffffffu, row1, j & 31);
-    if (idx < total) {
-      const int rj = j < 32 ? rj0 : rj1;
-      const int cc = c & 7;
-      const bf16* src = (c < 8 ? a.kc : a.vc) + ((long long)rj * a.T + j) * a.ldkv + h * HD + cc * 8;
-      cp_async_16(kv_base + (c < 8 ? 0 : 8192) + j * 128 + ((cc ^ (j & 7)) << 4), src);
-    }
-  }
-  cp_async_commit();
-  // V rows nk .. next multiple of 16 take part in the P.V MMAs with P = 0: they must be finite
-  {
-    const int pad_rows = ((nk + 15) & ~15) - nk;
-    for (int i = lane; i < pad_rows * 8; i += 32)
-      *reinterpret_cast<uint4*>(kv_smem + 8192 + (nk + (i >> 3)) * 128 + ((i & 7) << 4)) = make_uint4(0, 0, 0, 0);
-  }
-  // queries -> bf16 stage rows 0..rpk-1 (pre-scaled: 1/8 is exact), zero rows rpk..7; 64 16-byte chunks, 2 per lane
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int id = lane + t * 32;
-    const int rr = id >> 3, c8 = (id & 7) * 8;
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = 0.f;
-    if (rr < rpk && r0 + rr < a.R) {
-      const int r = r0 + rr;
-      if (a.q != nullptr) {
-        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
-      } else {
-        float* qa = a.q_acc + (long long)r * a.ldq + h * HD + c8;
-        float b[8];
-        load8f_cg(qa, f);
-        load8f(a.q_bias + h * HD + c8, b);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] + b[j]);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(qa) = z;                  // hand the split-K accumulator back zeroed
-        *reinterpret_cast<float4*>(qa + 4) = z;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] *= a.scale;
-    }
-    store8(q_stage + rr * QP + c8, f);
-  }
-  cp_async_wait_all();
-  __syncwarp();
-
+// S = Q K^T and the row softmax of the item's <= 8 query rows (stage row g = lane >> 2) over nk <= 64 keys.
+// Returns the un-normalised probabilities packed as the A fragments of the P V MMAs and 1 / row sum.
+__device__ __forceinline__ void attn_qk_softmax(uint32_t kv_base, const bf16* q_stage, int nk, int lane, uint32_t* pa,
+                                                float* inv_out) {
+  constexpr int QP = 72;
   const int g = lane >> 2, t4 = lane & 3;
   const int npairs = (nk + 15) >> 4;           // 16-key groups
-  // ---- S = Q K^T : rows g (0..7), 16-key groups
   float sacc[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f;
@@ -522,7 +468,6 @@ __device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int 
       }
     }
   }
-  // ---- softmax over the keys of row g (4 lanes share a row)
   float mx = -INFINITY;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
@@ -534,7 +479,6 @@ __device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int 
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
   float sum = 0.f;
-  uint32_t pa[8];
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const float p0 = __expf(sacc[n][0] - mx), p1 = __expf(sacc[n][1] - mx);     // exp(-inf) = 0 for masked keys
@@ -543,8 +487,14 @@ __device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int 
   }
   sum += __shfl_xor_sync(0xffffffffu, sum, 1);
   sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-  const float inv = 1.0f / sum;
-  // ---- O = P V : the S accumulator layout is the A-fragment layout of the next MMA (k = keys)
+  *inv_out = 1.0f / sum;
+}
+// O = P V (the S accumulator layout is the A-fragment layout of the next MMA, k = keys) and the bf16 store of the
+// rows_per_kv valid rows
+__device__ __forceinline__ void attn_pv_store(const DecAttnArgs& a, uint32_t kv_base, int nk, const uint32_t* pa,
+                                              float inv, int r0, int h, int lane) {
+  const int g = lane >> 2, t4 = lane & 3;
+  const int npairs = (nk + 15) >> 4;
   float oacc[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
@@ -565,7 +515,7 @@ __device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int 
       }
     }
   }
-  if (g < rpk && r0 + g < a.R) {
+  if (g < a.rows_per_kv && r0 + g < a.R) {
     const int r = r0 + g;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
@@ -574,7 +524,102 @@ __device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int 
       *reinterpret_cast<uint32_t*>(dst) = pack_bf16(oacc[n][0] * inv, oacc[n][1] * inv);
     }
   }
+}
+
+// cache rows of keys (lane, lane + 32) of an item: loaded one item ahead by the caller (hides the table latency)
+__device__ __forceinline__ void decode_attn_rows(const DecAttnArgs& a, int kv_item, int lane, int* row0, int* row1) {
+  *row0 = kv_item;
+  *row1 = kv_item;
+  if (a.anc) {
+    const int r0 = kv_item * a.rows_per_kv;
+    *row0 = lane < a.n_keys ? a.anc[(long long)r0 * a.T + lane] : 0;
+    *row1 = lane + 32 < a.n_keys ? a.anc[(long long)r0 * a.T + 32 + lane] : 0;
+  }
+}
+
+__device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int kv_item, int h, int row0, int row1,
+                                                      uint8_t* kv_smem, bf16* q_stage, int lane,
+                                                      unsigned long long* trace = nullptr) {
+  constexpr int QP = 72;                       // q_stage row pitch in elements
+  const int nk = a.n_keys;
+  const int rpk = a.rows_per_kv;
+  const int r0 = kv_item * rpk;
+  MIC_TRACE(0, row0 + row1)
+  // ---- query loads first (their latency hides behind the copy-issue loop): 64 16-byte chunks, 2 per lane
+  float qf[2][8];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int id = lane + t * 32;
+    const int rr = id >> 3, c8 = (id & 7) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qf[t][j] = 0.f;
+    if (rr < rpk && r0 + rr < a.R) {
+      const int r = r0 + rr;
+      if (a.q != nullptr) {
+        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, qf[t]);
+      } else {
+        load8f_cg(a.q_acc + (long long)r * a.ldq + h * HD + c8, qf[t]);
+      }
+    }
+  }
+  // ---- K / V rows -> stage: lanes 0..15 take the 16 chunks (8 K + 8 V) of an even key, lanes 16..31 of the odd
+  // key next to it; one shuffle and 32-bit offset arithmetic per copy (this loop is instruction-latency bound)
+  const uint32_t kv_base = smem_u32(kv_smem);
+  {
+    const int c = lane & 15, jsub = lane >> 4, cc = c & 7;
+    const bf16* src_base = (c < 8 ? a.kc : a.vc) + h * HD + cc * 8;
+    const uint32_t dst_base = kv_base + (c < 8 ? 0 : 8192);
+    const int ldkv = (int)a.ldkv, rowpitch = a.T * (int)a.ldkv;
+#pragma unroll 4
+    for (int j2 = 0; j2 < nk; j2 += 2) {
+      const int j = j2 + jsub;
+      const int rj = __shfl_sync(0xffffffffu, j2 < 32 ? row0 : row1, j & 31);
+      if (j < nk) cp_async_16(dst_base + j * 128 + ((cc ^ (j & 7)) << 4), src_base + (rj * rowpitch + j * ldkv));
+    }
+  }
+  cp_async_commit();
+  MIC_TRACE(1, nk)
+  // V rows nk .. next multiple of 16 take part in the P.V MMAs with P = 0: they must be finite
+  {
+    const int pad_rows = ((nk + 15) & ~15) - nk;
+    for (int i = lane; i < pad_rows * 8; i += 32)
+      *reinterpret_cast<uint4*>(kv_smem + 8192 + (nk + (i >> 3)) * 128 + ((i & 7) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  // queries -> bf16 stage rows 0..rpk-1 (pre-scaled: 1/8 is exact), zero rows rpk..7
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int id = lane + t * 32;
+    const int rr = id >> 3, c8 = (id & 7) * 8;
+    if (a.q == nullptr && rr < rpk && r0 + rr < a.R) {
+      float* qa = a.q_acc + (long long)(r0 + rr) * a.ldq + h * HD + c8;
+      float b[8];
+      load8f(a.q_bias + h * HD + c8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qf[t][j] = bf16_round(qf[t][j] + b[j]);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(qa) = z;                  // hand the split-K accumulator back zeroed
+      *reinterpret_cast<float4*>(qa + 4) = z;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qf[t][j] *= a.scale;
+    store8(q_stage + rr * QP + c8, qf[t]);
+  }
+  const int total = nk;
+  MIC_TRACE(2, total)
+  cp_async_wait_all();
+  __syncwarp();
+  MIC_TRACE(3, total)
+  uint32_t pa[8];
+  float inv;
+  attn_qk_softmax(kv_base, q_stage, nk, lane, pa, &inv);
+  MIC_TRACE(4, __float_as_int(inv))
+  attn_pv_store(a, kv_base, nk, pa, inv, r0, h, lane);
+  MIC_TRACE(5, nk)
   __syncwarp();     // the stages are refilled by the warp's next item
 }
+
+// (A software-pipelined variant that fetched every 128-byte key row with its own cp.async.bulk - cache rows stored
+//  pre-swizzled, next item's K requested right after S = Q K^T - was measured SLOWER: 24 us vs 20 us per
+//  self-attention phase; ~650 small bulk copies per SM per round queue up in the single TMA unit.)
 
 }  // namespace micdec

@@ -54,6 +54,7 @@ struct Phase {
   int act;                        // GEMM_STORE: activation after bias
   int col_split;                  // GEMM_STORE: columns >= col_split go to out2 (the K|V cache slot of this step)
   int out_tiled_kb;               // GEMM_STORE: > 0 -> `out` is a tile-image buffer with that many k blocks per row
+  int cache_swizzle;              // GEMM_STORE: cache rows are stored in the attention stage's chunk order (c ^ (pos & 7))
   const float* bias;              // GEMM_STORE: bias[N];  LN: bias of the GEMM that produced acc
   void* out;                      // GEMM_STORE: bf16 [R, ldo];  GEMM_RED / LN: fp32 accumulator [R, ldo]
   long long ldo;
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* attn_bar = bars + 2 * STAGES + 4;       // one per vector warp (self-attention bulk copies)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EW);
     }
+    for (int i = 0; i < EW; ++i) mbar_init(&attn_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -324,6 +327,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
                 }
                 if (!to_cache && ph.out_tiled_kb)
                   store8(reinterpret_cast<bf16*>(ph.out) + tiled_off(row, col0 + j, ph.out_tiled_kb), v + j);
+                else if (to_cache && ph.cache_swizzle)     // col0 % 32 == 0: chunk index (j >> 3) | (col0 & 32) >> 3
+                  store8(dst - (col0 & 63) + ((((((col0 & 63) + j) >> 3) ^ (args.pos & 7))) << 3), v + j);
                 else
                   store8(dst + j, v + j);
               }
@@ -395,8 +400,19 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           // host guarantees n_keys <= 64 and rows_per_kv <= 4 (mic_decoder_plan_init)
           const int items = ((a.R + a.rows_per_kv - 1) / a.rows_per_kv) * a.H;
 #pragma unroll 1
-          for (int i = gw; i < items; i += nw)
-            decode_attn_group_mma(a, i / a.H, i % a.H, kv_stage, reinterpret_cast<bf16*>(q_smem), lane);
+          const bool tra = args.prof && cta == TRACE_CTA && ew == 0 && p == 1 + 1 + 11 * 5;
+          if (tra && lane == 0) args.prof[(long long)P * G + 169] = gtime();
+          int row0 = 0, row1 = 0;
+          if (gw < items) decode_attn_rows(a, gw / a.H, lane, &row0, &row1);
+          for (int i = gw; i < items; i += nw) {
+            int nrow0 = 0, nrow1 = 0;
+            if (i + nw < items) decode_attn_rows(a, (i + nw) / a.H, lane, &nrow0, &nrow1);   // next item's table rows
+            decode_attn_group_mma(a, i / a.H, i % a.H, row0, row1, kv_stage, reinterpret_cast<bf16*>(q_smem), lane,
+                                  (tra && lane == 0) ? args.prof + (long long)P * G + 170 + 8 * ((i - gw) / nw) : nullptr);
+            row0 = nrow0;
+            row1 = nrow1;
+          }
+          if (tra && lane == 0) args.prof[(long long)P * G + 168] = gtime();
         }
       }
       // generic-proxy writes of this phase (tile-image activations in global memory, ring scratch in shared memory)

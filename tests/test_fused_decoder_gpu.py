@@ -22,7 +22,8 @@ def _run(engine, fused, enc_kv, R, T, K, tokens, anc_tables):
         hf = step(engine, cache, tokens[pos], pos)
         outs.append(hf.float().clone())
     torch.cuda.synchronize()
-    return torch.stack(outs), cache.self_kv.float().clone()
+    kv = cache.self_kv.float().clone()
+    return torch.stack(outs), kv
 
 
 @pytest.mark.parametrize("B,K", [(6, 4), (40, 4), (3, 1)])
