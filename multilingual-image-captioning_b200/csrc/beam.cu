@@ -46,9 +46,19 @@ search_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ ps
     const long long o = (long long)p * R + r;
     const float m = pmax[o];
     if (m > -INFINITY) sm += psum[o] * __expf(m - mx);
+    // the whole sorted list of this slab in four 16-byte loads (one round trip instead of up to eight)
+    float lv[TOPK];
+    int li[TOPK];
+    {
+      const float4 v0 = *reinterpret_cast<const float4*>(cval + o * TOPK), v1 = *reinterpret_cast<const float4*>(cval + o * TOPK + 4);
+      const int4 i0 = *reinterpret_cast<const int4*>(cidx + o * TOPK), i1 = *reinterpret_cast<const int4*>(cidx + o * TOPK + 4);
+      lv[0] = v0.x; lv[1] = v0.y; lv[2] = v0.z; lv[3] = v0.w; lv[4] = v1.x; lv[5] = v1.y; lv[6] = v1.z; lv[7] = v1.w;
+      li[0] = i0.x; li[1] = i0.y; li[2] = i0.z; li[3] = i0.w; li[4] = i1.x; li[5] = i1.y; li[6] = i1.z; li[7] = i1.w;
+    }
+#pragma unroll
     for (int e = 0; e < TOPK; ++e) {
-      float cv = cval[o * TOPK + e];
-      int ci = cidx[o * TOPK + e];
+      float cv = lv[e];
+      int ci = li[e];
       if (!better(cv, ci, tv[TOPK - 1], ti[TOPK - 1])) break;   // list is sorted: nothing further can enter
 #pragma unroll
       for (int i = 0; i < TOPK; ++i) {
@@ -101,6 +111,25 @@ search_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ ps
   }
 }
 
+// lane id of the best (value desc, key asc) among the lanes with valid == true (all lanes get the same answer);
+// -1 if none.  -inf candidates are legal entries (ForcedBOS fillers), hence the separate validity flag.
+__device__ __forceinline__ int warp_best(float v, int key, bool valid, int lane) {
+  float bv = v;
+  int bk = key, bl = valid ? lane : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (ol >= 0 && (bl < 0 || better(ov, ok, bv, bk))) {
+      bv = ov;
+      bk = ok;
+      bl = ol;
+    }
+  }
+  return bl;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Beam step: one warp per image.  State arrays follow the reference's BeamSearchState.
 // ---------------------------------------------------------------------------------------------
@@ -133,7 +162,7 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const BeamArgs a) {
   int* old_run = sh;                    // [K, L]
   int* old_seq = sh + K * L;            // [K, L]
   int* old_anc = sh + 2 * K * L;        // [K, L]
-  __shared__ float s_tlp[TOPK], s_tlp2[TOPK], s_newscore[MAX_BEAMS], s_newrun[MAX_BEAMS];
+  __shared__ float s_tlp[TOPK], s_tlp2[MAX_BEAMS + TOPK], s_newscore[MAX_BEAMS], s_newrun[MAX_BEAMS];
   __shared__ int s_beam[TOPK], s_tok[TOPK], s_fin[TOPK], s_runsel[MAX_BEAMS], s_mergesel[MAX_BEAMS], s_newfin[MAX_BEAMS];
   for (int i = lane; i < K * L; i += 32) {
     old_run[i] = a.running_seq[(long long)b * K * L + i];
@@ -141,81 +170,90 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const BeamArgs a) {
     if (a.ancestors) old_anc[i] = a.ancestors[(long long)b * K * L + i];
   }
   __syncwarp();
-  if (lane == 0) {
+  // ---- 3..7 run warp-parallel: one candidate per lane, selections by warp arg-max rounds (the statement order and
+  // every fp32 operation of the reference are kept; only WHO evaluates them changed - a single-lane version with
+  // local-memory candidate arrays cost 36 us per step)
+  {
     // ---- 3. top 2K over the K*V candidates (value desc, flat index asc) ----
-    float cv[MAX_BEAMS * TOPK];
-    int cflat[MAX_BEAMS * TOPK];
-    int n = 0;
+    float cv = -INFINITY;
+    int cflat = 0x7fffffff;
+    bool valid = false;
     if (a.forced_token >= 0) {
-      for (int k = 0; k < K; ++k) {
-        cv[n] = 0.0f + a.running_scores[b * K + k];
-        cflat[n++] = k * a.V + a.forced_token;
-      }
-      for (int f = 0; n < 2 * K + K && f < a.V; ++f) {          // -inf fillers: lowest flat indices
-        if (f == a.forced_token) continue;
-        cv[n] = -INFINITY;
-        cflat[n++] = f;
-      }
-    } else {
-      for (int k = 0; k < K; ++k)
-        for (int e = 0; e < TOPK; ++e) {
-          cv[n] = a.row_lp[((long long)b * K + k) * TOPK + e] + a.running_scores[b * K + k];
-          cflat[n++] = k * a.V + a.row_tok[((long long)b * K + k) * TOPK + e];
+      if (lane < K) {                                   // the forced id of every beam: log-prob 0
+        cv = 0.0f + a.running_scores[b * K + lane];
+        cflat = lane * a.V + a.forced_token;
+        valid = true;
+      } else if (lane < 3 * K) {                        // -inf fillers: lowest flat indices other than the forced id
+        int f = lane - K;
+        if (f >= a.forced_token) ++f;
+        if (f < a.V) {
+          cflat = f;
+          valid = true;
         }
+      }
+    } else if (lane < K * TOPK) {
+      const int k = lane / TOPK;
+      cv = a.row_lp[(long long)b * K * TOPK + lane] + a.running_scores[b * K + k];
+      cflat = k * a.V + a.row_tok[(long long)b * K * TOPK + lane];
+      valid = true;
     }
-    bool used[MAX_BEAMS * TOPK];
-    for (int i = 0; i < n; ++i) used[i] = false;
+    // lane j (< 2K) ends up holding candidate j of the ordered top-2K list
+    float my_tlp = 0.f;
+    int my_flat = 0;
     for (int j = 0; j < K2; ++j) {
-      int best = -1;
-      for (int i = 0; i < n; ++i)
-        if (!used[i] && (best < 0 || better(cv[i], cflat[i], cv[best], cflat[best]))) best = i;
-      used[best] = true;
-      s_tlp[j] = cv[best];
-      s_beam[j] = cflat[best] / a.V;
-      s_tok[j] = cflat[best] % a.V;
-      // ---- 4. did_topk_just_finished ; topk_log_probs += finished * -1e7 ----
-      s_fin[j] = (s_tok[j] == a.eos) ? 1 : 0;
-      s_tlp[j] = s_tlp[j] + (s_fin[j] ? NEG_BIG : -0.0f);
+      const int w = warp_best(cv, cflat, valid, lane);
+      const float wv = __shfl_sync(0xffffffffu, cv, w);
+      const int wf = __shfl_sync(0xffffffffu, cflat, w);
+      if (lane == w) valid = false;
+      if (lane == j) {
+        my_tlp = wv;
+        my_flat = wf;
+      }
     }
-    // ---- 5. next running = top K of the 2K (stable), flipped to ascending ----
-    bool u2[TOPK];
-    for (int i = 0; i < K2; ++i) u2[i] = false;
+    const int my_beam = my_flat / a.V, my_tok = my_flat % a.V;
+    // ---- 4. did_topk_just_finished ; topk_log_probs += finished * -1e7 ----
+    const int my_fin = (my_tok == a.eos) ? 1 : 0;
+    my_tlp = my_tlp + (my_fin ? NEG_BIG : -0.0f);
+    if (lane < K2) {
+      s_tlp[lane] = my_tlp;
+      s_beam[lane] = my_beam;
+      s_tok[lane] = my_tok;
+      s_fin[lane] = my_fin;
+    }
+    // ---- 5. next running = top K of the 2K (stable: strict > keeps the lower index), flipped to ascending ----
+    bool v5 = lane < K2;
     for (int j = 0; j < K; ++j) {
-      int best = -1;
-      for (int i = 0; i < K2; ++i)
-        if (!u2[i] && (best < 0 || s_tlp[i] > s_tlp[best])) best = i;   // strict > keeps lower index on ties
-      u2[best] = true;
-      s_runsel[K - 1 - j] = best;
+      const int w = warp_best(my_tlp, lane, v5, lane);
+      if (lane == w) v5 = false;
+      if (lane == 0) s_runsel[K - 1 - j] = w;
     }
-    for (int k = 0; k < K; ++k) s_newrun[k] = s_tlp[s_runsel[k]];
+    __syncwarp();
+    if (lane < K) s_newrun[lane] = s_tlp[s_runsel[lane]];
     // ---- 6. length penalty on the (already penalised) array, then the second penalty ----
     bool all_fin = true;
     for (int k = 0; k < K; ++k) all_fin = all_fin && (a.finished[b * K + k] != 0);
     const bool beams_full = all_fin && a.early_stopping;
     const float denom = powf((float)a.cur_len, a.length_penalty);
-    for (int j = 0; j < K2; ++j) {
-      float v = s_tlp[j] / denom;
-      const bool add_pen = (!s_fin[j]) || beams_full;
-      v = v + (add_pen ? NEG_BIG : -0.0f);
-      s_tlp2[j] = v;
-    }
+    float my_tlp2 = my_tlp / denom;
+    my_tlp2 = my_tlp2 + (((!my_fin) || beams_full) ? NEG_BIG : -0.0f);
     // ---- 7. merge with the finished set: top K of (K old + 2K new), stable, flipped ----
-    float mv[MAX_BEAMS + TOPK];
-    for (int k = 0; k < K; ++k) mv[k] = a.scores[b * K + k];
-    for (int j = 0; j < K2; ++j) mv[K + j] = s_tlp2[j];
-    bool u3[MAX_BEAMS + TOPK];
-    for (int i = 0; i < K + K2; ++i) u3[i] = false;
+    const float shifted = __shfl_sync(0xffffffffu, my_tlp2, (lane - K) & 31);      // lane l >= K takes candidate l - K
+    float mv = -INFINITY;
+    bool v7 = lane < K + K2;
+    if (lane < K) mv = a.scores[b * K + lane];
+    else if (v7) mv = shifted;
     for (int j = 0; j < K; ++j) {
-      int best = -1;
-      for (int i = 0; i < K + K2; ++i)
-        if (!u3[i] && (best < 0 || mv[i] > mv[best])) best = i;
-      u3[best] = true;
-      s_mergesel[K - 1 - j] = best;
+      const int w = warp_best(mv, lane, v7, lane);
+      if (lane == w) v7 = false;
+      if (lane == 0) s_mergesel[K - 1 - j] = w;
     }
-    for (int k = 0; k < K; ++k) {
-      const int m = s_mergesel[k];
-      s_newscore[k] = mv[m];
-      s_newfin[k] = m < K ? a.finished[b * K + m] : s_fin[m - K];
+    __syncwarp();
+    if (lane < K + K2) s_tlp2[lane] = mv;              // merged value list (reusing s_tlp2 as [K + 2K] needs 12 slots)
+    __syncwarp();
+    if (lane < K) {
+      const int m = s_mergesel[lane];
+      s_newscore[lane] = s_tlp2[m];
+      s_newfin[lane] = m < K ? a.finished[b * K + m] : s_fin[m - K];
     }
   }
   __syncwarp();

@@ -345,52 +345,54 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         }
         if (ph.kind == PH_LN) {
-          // x += acc + bias; y = LN(x); acc = 0.  One row per CTA at a time, all 256 vector threads on it (4 columns
-          // each): a lone warp per row is instruction-latency bound (5 us per row measured), this is ~1 us.
+          // x += acc + bias; y = LN(x); acc = 0.  Two rows per CTA at a time, 128 vector threads (8 columns each)
+          // per row: a lone warp per row is instruction-latency bound (5 us per row measured).
           float* acc = reinterpret_cast<float*>(ph.out);
-          const int d = ph.d, c = vt * 4;
+          const int d = ph.d;
+          const int sel = vt >> 7, c = (vt & 127) * 8;           // which row of the pair, first column
           int par = 0;
-          for (int row = cta; row < args.R; row += G, par ^= 1) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f}, g[4], be[4];
+          for (int rowa = cta; rowa < args.R; rowa += 2 * G, par ^= 1) {
+            const int row = rowa + sel * G;
+            const bool on = row < args.R && c < d;
+            float v[8], g[8], be[8];
             float s = 0.f, s2 = 0.f;
-            if (c < d) {
-              const uint2 xr = __ldcg(reinterpret_cast<const uint2*>(ph.x + (long long)row * d + c));
-              const float4 ar = __ldcg(reinterpret_cast<const float4*>(acc + (long long)row * d + c));
-              const float4 br = *reinterpret_cast<const float4*>(ph.bias + c);
-              const float4 gr = *reinterpret_cast<const float4*>(ph.gamma + c);
-              const float4 er = *reinterpret_cast<const float4*>(ph.beta + c);
-              g[0] = gr.x; g[1] = gr.y; g[2] = gr.z; g[3] = gr.w;
-              be[0] = er.x; be[1] = er.y; be[2] = er.z; be[3] = er.w;
-              const float2 x01 = unpack_bf16(xr.x), x23 = unpack_bf16(xr.y);
-              v[0] = bf16_round(x01.x + ar.x + br.x);
-              v[1] = bf16_round(x01.y + ar.y + br.y);
-              v[2] = bf16_round(x23.x + ar.z + br.z);
-              v[3] = bf16_round(x23.y + ar.w + br.w);
-              *reinterpret_cast<uint2*>(ph.x + (long long)row * d + c) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-              *reinterpret_cast<float4*>(acc + (long long)row * d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-              s = v[0] + v[1] + v[2] + v[3];
-              s2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+            if (on) {
+              float ar[8], br[8];
+              load8_cg(ph.x + (long long)row * d + c, v);
+              load8f_cg(acc + (long long)row * d + c, ar);
+              load8f(ph.bias + c, br);
+              load8f(ph.gamma + c, g);
+              load8f(ph.beta + c, be);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j] = bf16_round(v[j] + ar[j] + br[j]);
+                s += v[j];
+                s2 += v[j] * v[j];
+              }
+              store8(ph.x + (long long)row * d + c, v);
+              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(acc + (long long)row * d + c) = z;
+              *reinterpret_cast<float4*>(acc + (long long)row * d + c + 4) = z;
             }
             s = warp_sum(s);
             s2 = warp_sum(s2);
             if (lane == 0) {
-              ln_part[par * 16 + ew * 2] = s;
+              ln_part[par * 16 + ew * 2] = s;                    // warps 0..3 -> row a, 4..7 -> row b
               ln_part[par * 16 + ew * 2 + 1] = s2;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
             float ts = 0.f, ts2 = 0.f;
 #pragma unroll
-            for (int w = 0; w < EW; ++w) {
-              ts += ln_part[par * 16 + w * 2];
-              ts2 += ln_part[par * 16 + w * 2 + 1];
+            for (int w = 0; w < EW / 2; ++w) {
+              ts += ln_part[par * 16 + (sel * 4 + w) * 2];
+              ts2 += ln_part[par * 16 + (sel * 4 + w) * 2 + 1];
             }
             const float mean = ts / d;
             const float rstd = rsqrtf(fmaxf(ts2 / d - mean * mean, 0.f) + ph.eps);
-            if (c < d) {
-              const float o0 = (v[0] - mean) * rstd * g[0] + be[0], o1 = (v[1] - mean) * rstd * g[1] + be[1];
-              const float o2 = (v[2] - mean) * rstd * g[2] + be[2], o3 = (v[3] - mean) * rstd * g[3] + be[3];
-              bf16* yp = ph.y + (ph.y_tiled_kb ? tiled_off(row, c & ~7, ph.y_tiled_kb) + (c & 7) : (long long)row * d + c);
-              *reinterpret_cast<uint2*>(yp) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+            if (on) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + be[j];
+              store8(ph.y + (ph.y_tiled_kb ? tiled_off(row, c, ph.y_tiled_kb) : (long long)row * d + c), v);
             }
           }
         } else {
