@@ -364,8 +364,8 @@ struct EpiCEStats {
     const float nm2 = nm * MIC_LOG2E;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc += exp2f(fmaf(v[j], MIC_LOG2E, -nm2));
-    st.sm = st.sm * exp2f((st.mx - nm) * MIC_LOG2E) + acc;
+    for (int j = 0; j < 64; ++j) acc += ex2_approx(fmaf(v[j], MIC_LOG2E, -nm2));
+    st.sm = st.sm * ex2_approx((st.mx - nm) * MIC_LOG2E) + acc;
     st.mx = nm;
     if (p.store_logits) {
       stg_acquire<0>(ctx.lane);
@@ -438,7 +438,7 @@ struct EpiCEGrad {
     }
     const float lw = p.low * st.w;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = fmaf(exp2f(fmaf(v[j], MIC_LOG2E, -st.lse2)), st.w, -lw);
+    for (int j = 0; j < 64; ++j) v[j] = fmaf(ex2_approx(fmaf(v[j], MIC_LOG2E, -st.lse2)), st.w, -lw);
     if (!full) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = (col0 + j < s.N) ? v[j] : 0.f;     // padded vocab columns: exactly zero
@@ -557,8 +557,8 @@ struct EpiSearch {
     const float nm2 = nm * MIC_LOG2E;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc += exp2f(fmaf(v[j], MIC_LOG2E, -nm2));
-    st.sm = st.sm * exp2f((st.mx - nm) * MIC_LOG2E) + acc;
+    for (int j = 0; j < 64; ++j) acc += ex2_approx(fmaf(v[j], MIC_LOG2E, -nm2));
+    st.sm = st.sm * ex2_approx((st.mx - nm) * MIC_LOG2E) + acc;
     st.mx = nm;
   }
   __device__ static void kernel_end(const Params& p, State& st, const Shape& s, int row, int slot) {
