@@ -710,8 +710,8 @@ __global__ void __launch_bounds__(128) attention_bwd_dkv_kernel(const AttnArgs a
 __global__ void __launch_bounds__(128) decode_attention_kernel(const DecAttnArgs a) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float s_p[4][128];
-  __shared__ int s_row[4][128];
+  __shared__ float s_p[4][micdec::DEC_MAX_KEYS];
+  __shared__ int s_row[4][micdec::DEC_MAX_KEYS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int wid = blockIdx.x * 4 + w;
   if (wid >= a.R * a.H) return;
@@ -808,7 +808,7 @@ extern "C" int mic_decode_attention(void* stream, const void* q, long long ldq, 
                                     int n_keys, int rows_per_kv, void* o, long long ldo, int R, int H, int head_dim,
                                     float scale) {
   MIC_CHECK_ARG(head_dim == HD, "decode attention: head_dim %d != 64", head_dim);
-  MIC_CHECK_ARG(n_keys >= 1 && n_keys <= 128 && n_keys <= cache_len, "decode attention: n_keys=%d cache_len=%d",
+  MIC_CHECK_ARG(n_keys >= 1 && n_keys <= micdec::DEC_MAX_KEYS && n_keys <= cache_len, "decode attention: n_keys=%d (max 256) cache_len=%d",
                 n_keys, cache_len);
   DecAttnArgs a;
   a.q = (const bf16*)q; a.ldq = ldq; a.kc = (const bf16*)k_cache; a.vc = (const bf16*)v_cache; a.ldkv = ldkv;

@@ -6,6 +6,7 @@
 namespace micdec {
 
 constexpr int HD = 64;            // head dim
+constexpr int DEC_MAX_KEYS = 256; // per-op cached attention: keys per row (model default max_length is 200)
 constexpr int LN_MAX_ITERS = 4;   // features <= 1024 (32 lanes * 8 elements * 4)
 
 __device__ __forceinline__ void load8(const bf16* p, float* x) {
@@ -179,7 +180,7 @@ struct DecAttnArgs {
   long long ldkv;
   const int* anc;        // [R, T] ancestor rows or null (identity)
   int T;                 // cache length (positions per row)
-  int n_keys;            // keys to attend (cur position + 1) or S for cross (<= 128)
+  int n_keys;            // keys to attend (cur position + 1) or S for cross (<= DEC_MAX_KEYS)
   int rows_per_kv;       // cross-attention: beams per image (kv row = r / rows_per_kv); 1 otherwise
   bf16* o;               // [R, ldo]
   long long ldo;
@@ -192,7 +193,7 @@ struct DecAttnArgs {
   int o_tiled_kb;        // > 0: o is written in the UMMA tile image layout (tiled_off), = H
 };
 
-// s_p: 128 floats, s_row: 128 ints of per-warp shared scratch.  q / k / v go through L2 (ld.global.cg): in the
+// s_p: DEC_MAX_KEYS floats, s_row: DEC_MAX_KEYS ints of per-warp shared scratch.  q / k / v go through L2 (ld.global.cg): in the
 // persistent kernel the newest position was written by another SM within the same launch.
 __device__ __forceinline__ void decode_attn_item(const DecAttnArgs& a, int r, int h, float* s_p, int* s_row,
                                                  int lane) {
@@ -228,9 +229,9 @@ __device__ __forceinline__ void decode_attn_item(const DecAttnArgs& a, int r, in
   __syncwarp();
   // scores: lane handles keys lane, lane+32, ... (8 independent 16-byte loads per key)
   float mx = -INFINITY;
-  float sc[4];
+  float sc[DEC_MAX_KEYS / 32];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < DEC_MAX_KEYS / 32; ++i) {
     const int j = lane + i * 32;
     float sdot = -INFINITY;
     if (j < nk) {
@@ -257,7 +258,7 @@ __device__ __forceinline__ void decode_attn_item(const DecAttnArgs& a, int r, in
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < DEC_MAX_KEYS / 32; ++i) {
     const int j = lane + i * 32;
     const float p = (j < nk) ? __expf(sc[i] - mx) : 0.f;
     if (j < nk) s_p[j] = p;

@@ -226,7 +226,11 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
     enc = engine.encode(px, trunc_int=True, save=False, tag="gen.enc")
     enc_kv = engine.cross_kv(enc, tag="gen.enc")
     cache = DecodeCache(engine, R, Lmax, enc_kv, K, use_ancestors=K > 1)
-    if getattr(engine, "fused_decoder", True):
+    # the persistent decoder-step kernel stages <= 64 keys per attention item and <= 4 beams per image; longer
+    # searches (the model default max_length is 200) take the per-op path
+    fused_ok = (Lmax <= 64 and engine.c.num_tokens <= 64 and K <= 4 and t.pre_layernorm and t.final_layer_norm
+                and t.activation_function == "gelu" and t.decoder_layers <= 12)
+    if getattr(engine, "fused_decoder", True) and fused_ok:
         cache.fused = fused_prepare(engine, cache, packed_search=True)     # plan + this call's packed weights
     ws = _search_ws(engine, R)
     active = torch.ones(1, dtype=I32, device=dev)
