@@ -619,6 +619,83 @@ __device__ __forceinline__ void decode_attn_group_mma(const DecAttnArgs& a, int 
   __syncwarp();     // the stages are refilled by the warp's next item
 }
 
+// ---------------------------------------------------------------------------------------------
+// Self-attention items of one warp (rows_per_kv == 1), software-pipelined on the ONE 16 KB stage: the next item's
+// K rows are requested (cp.async) as soon as S = Q K^T has consumed the stage's K half, its V rows after P V, so an
+// item's HBM round trip runs under the previous item's math instead of in front of its own.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void attn_issue_operand(const DecAttnArgs& a, const bf16* base, int h, int row0, int row1,
+                                                   uint32_t dst_base, int lane) {
+  // 4 keys per instruction: lane = (key offset 0..3, 16-byte chunk 0..7)
+  const int nk = a.n_keys;
+  const int cc = lane & 7, jsub = lane >> 3;
+  const bf16* src_base = base + h * HD + cc * 8;
+  const int ldkv = (int)a.ldkv, rowpitch = a.T * (int)a.ldkv;
+#pragma unroll 4
+  for (int j4 = 0; j4 < nk; j4 += 4) {
+    const int j = j4 + jsub;
+    const int rj = __shfl_sync(0xffffffffu, j4 < 32 ? row0 : row1, j & 31);
+    if (j < nk) cp_async_16(dst_base + j * 128 + ((cc ^ (j & 7)) << 4), src_base + (rj * rowpitch + j * ldkv));
+  }
+}
+
+__device__ __forceinline__ void decode_self_attn_pipelined(const DecAttnArgs& a, int first, int stride, int items,
+                                                           uint8_t* kv_smem, bf16* q_stage, int lane) {
+  constexpr int QP = 72;
+  const int nk = a.n_keys;
+  const uint32_t kv_base = smem_u32(kv_smem);
+  int i = first;
+  if (i >= items) return;
+  {   // V rows nk .. next multiple of 16 take part in the P.V MMAs with P = 0: they must be finite (never overwritten)
+    const int pad_rows = ((nk + 15) & ~15) - nk;
+    for (int t = lane; t < pad_rows * 8; t += 32)
+      *reinterpret_cast<uint4*>(kv_smem + 8192 + (nk + (t >> 3)) * 128 + ((t & 7) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  int row0, row1;
+  decode_attn_rows(a, i / a.H, lane, &row0, &row1);
+  attn_issue_operand(a, a.kc, i % a.H, row0, row1, kv_base, lane);
+  attn_issue_operand(a, a.vc, i % a.H, row0, row1, kv_base + 8192, lane);
+  cp_async_commit();
+  while (true) {
+    const int r = i / a.H, h = i % a.H;
+    const int inext = i + stride;
+    const bool has_next = inext < items;
+    int nrow0 = 0, nrow1 = 0;
+    if (has_next) decode_attn_rows(a, inext / a.H, lane, &nrow0, &nrow1);
+    // query row -> bf16 stage row 0 (pre-scaled: 1/8 is exact), rows 1..7 zero: 64 chunks, 2 per lane
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int id = lane + t * 32;
+      const int rr = id >> 3, c8 = (id & 7) * 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      if (rr == 0) {
+        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= a.scale;
+      }
+      store8(q_stage + rr * QP + c8, f);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t pa[8];
+    float inv;
+    attn_qk_softmax(kv_base, q_stage, nk, lane, pa, &inv);
+    __syncwarp();                                   // every lane is done with the K half (and the query stage)
+    if (has_next) {
+      attn_issue_operand(a, a.kc, inext % a.H, nrow0, nrow1, kv_base, lane);
+      cp_async_commit();
+    }
+    attn_pv_store(a, kv_base, nk, pa, inv, r, h, lane);
+    __syncwarp();                                   // ... and with the V half
+    if (!has_next) break;
+    attn_issue_operand(a, a.vc, inext % a.H, nrow0, nrow1, kv_base + 8192, lane);
+    cp_async_commit();
+    i = inext;
+  }
+}
+
 // (A software-pipelined variant that fetched every 128-byte key row with its own cp.async.bulk - cache rows stored
 //  pre-swizzled, next item's K requested right after S = Q K^T - was measured SLOWER: 24 us vs 20 us per
 //  self-attention phase; ~650 small bulk copies per SM per round queue up in the single TMA unit.)

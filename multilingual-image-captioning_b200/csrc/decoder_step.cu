@@ -404,15 +404,15 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
 #pragma unroll 1
           const bool tra = args.prof && cta == TRACE_CTA && ew == 0 && p == 1 + 1 + 11 * 5;
           if (tra && lane == 0) args.prof[(long long)P * G + 169] = gtime();
-          int row0 = 0, row1 = 0;
-          if (gw < items) decode_attn_rows(a, gw / a.H, lane, &row0, &row1);
-          for (int i = gw; i < items; i += nw) {
-            int nrow0 = 0, nrow1 = 0;
-            if (i + nw < items) decode_attn_rows(a, (i + nw) / a.H, lane, &nrow0, &nrow1);   // next item's table rows
-            decode_attn_group_mma(a, i / a.H, i % a.H, row0, row1, kv_stage, reinterpret_cast<bf16*>(q_smem), lane,
-                                  (tra && lane == 0) ? args.prof + (long long)P * G + 170 + 8 * ((i - gw) / nw) : nullptr);
-            row0 = nrow0;
-            row1 = nrow1;
+          if (ph.keys_from_pos && a.q != nullptr) {
+            decode_self_attn_pipelined(a, gw, nw, items, kv_stage, reinterpret_cast<bf16*>(q_smem), lane);
+          } else {
+            for (int i = gw; i < items; i += nw) {
+              int row0, row1;
+              decode_attn_rows(a, i / a.H, lane, &row0, &row1);
+              decode_attn_group_mma(a, i / a.H, i % a.H, row0, row1, kv_stage, reinterpret_cast<bf16*>(q_smem), lane,
+                                    nullptr);
+            }
           }
           if (tra && lane == 0) args.prof[(long long)P * G + 168] = gtime();
         }
