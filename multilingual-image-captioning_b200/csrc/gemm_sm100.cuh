@@ -533,7 +533,10 @@ struct EpiSearch {
     if (cmax > st.tv[SEARCH_TOPK - 1]) {
       // rare once the running threshold has risen: sorted insert (descending; strict > keeps the lower
       // index ahead on ties because columns are visited in ascending order)
-#pragma unroll 8
+      // FULLY unrolled on purpose: a partially unrolled scan indexes v[] dynamically, which put the whole 64-float
+      // group into local memory (256-byte stack frame) and made this epilogue - not the 512 MB weight stream -
+      // the bound of the search kernel
+#pragma unroll
       for (int j = 0; j < 64; ++j) {
         if (v[j] > st.tv[SEARCH_TOPK - 1]) {
           float cv = v[j];
