@@ -21,22 +21,39 @@ BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 
 
 class _Bufs:
-    """Lazily allocated, shape-keyed device buffers (allocated once per plan, reused every step)."""
+    """Lazily allocated device buffers, addressed by name.  `t[name]` is the buffer last requested under that name;
+    every (name, shape, dtype) ever requested stays allocated at a stable address, because captured CUDA graphs
+    (train step, generate loop) hold raw pointers to them: re-requesting a name with another shape must not free
+    the tensor an older graph still replays on."""
 
     def __init__(self, device):
         self.device = device
         self.t = {}
+        self.pool = {}
 
     def get(self, name, shape, dtype=BF16):
-        key = name
-        t = self.t.get(key)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
-            self.t[key] = t
+        shape = tuple(shape)
+        t = self.t.get(name)
+        if t is not None and tuple(t.shape) == shape and t.dtype == dtype:
+            return t
+        key = (name, shape, dtype)
+        t = self.pool.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.pool[key] = t
+        self.t[name] = t
         return t
 
+    def zeros(self, name, shape, dtype=F32):
+        """Like get(), but zero-filled when first allocated (accumulators that their kernels hand back zeroed)."""
+        key = (name, tuple(shape), dtype)
+        if key not in self.pool:
+            self.pool[key] = torch.zeros(tuple(shape), dtype=dtype, device=self.device)
+        self.t[name] = self.pool[key]
+        return self.pool[key]
+
     def nbytes(self):
-        return sum(x.numel() * x.element_size() for x in self.t.values())
+        return sum(x.numel() * x.element_size() for x in self.pool.values())
 
 
 class CaptionEngine:

@@ -56,10 +56,7 @@ def decode_step(engine, cache: DecodeCache, tokens, pos: int):
     q = b.get("gen.q", (R, d))
     o = b.get("gen.o", (R, d))
     g = b.get("gen.g", (R, t.decoder_ffn_dim))
-    acc = b.t.get("gen.acc")
-    if acc is None or tuple(acc.shape) != (R, d):
-        acc = torch.zeros((R, d), dtype=F32, device=engine.dev)      # zeroed once; kernels hand it back zeroed
-        b.t["gen.acc"] = acc
+    acc = b.zeros("gen.acc", (R, d))                                 # zeroed once; kernels hand it back zeroed
     sk_d = max(1, min(4, d // 256))
     sk_f = max(1, min(8, t.decoder_ffn_dim // 512))
     L2 = L * 2 * d
@@ -113,18 +110,16 @@ def _fused_plan(engine, cache: DecodeCache, tiled_out=False):
             "ln_out_g": ps.f("d.ln_final.scale"), "ln_out_b": ps.f("d.ln_final.bias"),
             "h_out_tiles": _aligned(engine, "gen.h_tiles", Rp * d * 2) if tiled_out else None}
     for n in ("acc", "q_acc"):
-        z = b.t.get("gen." + n)
-        if z is None or tuple(z.shape) != (R, d):
-            z = torch.zeros((R, d), dtype=F32, device=engine.dev)     # zeroed once; the kernel hands it back zeroed
-            b.t["gen." + n] = z
-        bufs[n] = z
+        bufs[n] = b.zeros("gen." + n, (R, d))                        # zeroed once; the kernel hands it back zeroed
     packed = _aligned(engine, "gen.wpack", ops.decoder_packed_bytes(L, d, F))
     key = (R, T, tiled_out, cache.rows_per_image, cache.enc_kv.data_ptr(), cache.self_kv.data_ptr(), ps.shadow.data_ptr(),
            ps.master.data_ptr(), packed.data_ptr()) + tuple(0 if v is None else v.data_ptr() for v in bufs.values())
+    # every plan ever built stays alive: captured generate() graphs replay on its device buffers
     plans = engine.__dict__.setdefault("_fused_plans", {})
-    entry = plans.get("decoder")
-    if entry is not None and entry[0] == key:
-        return entry[1]
+    entry = plans.get(key)
+    if entry is not None:
+        plans["decoder"] = (key, entry)
+        return entry
     assert not torch.cuda.is_current_stream_capturing(), "fused decoder plan must be built before graph capture"
     layers = []
     for l in range(L):
@@ -151,7 +146,8 @@ def _fused_plan(engine, cache: DecodeCache, tiled_out=False):
     ops.decoder_plan_init(plan, lstruct, bufs, packed, R, d, t.decoder_attention_heads, F, T, engine.c.num_tokens,
                           cache.rows_per_image, L * 2 * d, t.activation_function, t.layer_norm_eps)
     fp = {"plan": plan, "sync": sync, "bufs": bufs, "layers": lstruct, "packed": packed}
-    plans["decoder"] = (key, fp)
+    plans[key] = fp
+    plans["decoder"] = (key, fp)           # most recent (tests / tools)
     return fp
 
 
@@ -230,8 +226,9 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
     # searches (the model default max_length is 200) take the per-op path
     fused_ok = (Lmax <= 64 and engine.c.num_tokens <= 64 and K <= 4 and t.pre_layernorm and t.final_layer_norm
                 and t.activation_function == "gelu" and t.decoder_layers <= 12)
-    if getattr(engine, "fused_decoder", True) and fused_ok:
-        cache.fused = fused_prepare(engine, cache, packed_search=True)     # plan + this call's packed weights
+    import os
+    if getattr(engine, "fused_decoder", True) and fused_ok and os.environ.get("MIC_FUSED_DECODER", "1") != "0":
+        cache.fused = fused_prepare(engine, cache, packed_search=os.environ.get("MIC_PACKED_SEARCH", "1") != "0")
     ws = _search_ws(engine, R)
     active = torch.ones(1, dtype=I32, device=dev)
     next_token = torch.full((R,), decoder_start_token_id, dtype=I32, device=dev)

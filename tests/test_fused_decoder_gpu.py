@@ -103,3 +103,29 @@ def test_long_generation_takes_the_per_op_path_and_matches_the_oracle_prefix():
     assert (out[:, :2] == ref_seq[:, :2]).all()
     agree = (out == ref_seq).mean()
     assert agree > 0.5, agree          # bf16 drift may fork a row late; the bulk of 150 positions still agrees
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_graph_replay_survives_other_shapes_and_new_params(fused):
+    """A captured generate() graph holds raw pointers: running another search shape in between (which re-requests
+    the decode buffers with other shapes) and changing the parameters must not invalidate its replay."""
+    cfg = mic_b200.tiny_config()
+    model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, seed=3)
+    model.engine.fused_decoder = fused
+    px = torch.from_numpy(synthetic.make_batch(cfg, 5, 16, seed=2)["pixel_values"]).cuda()
+    kw_a = dict(max_length=12, pad_token_id=1, eos_token_id=2, decoder_start_token_id=2, num_beams=1, min_length=0,
+                forced_bos_token_id=7, forced_eos_token_id=2, length_penalty=1.0, early_stopping=True)
+    kw_b = dict(kw_a, max_length=2)
+    kw_c = dict(kw_a, num_beams=3, max_length=7)
+    p1 = synthetic.make_params(cfg, seed=5, perturbed=True, std=0.12)
+    p2 = synthetic.make_params(cfg, seed=6, perturbed=True, std=0.12)
+    p2["final_logits_bias"] = p2["final_logits_bias"].copy()
+    p2["final_logits_bias"][0, 2] += 5.0
+    model.params = p1
+    gen.generate(model.engine, px, **kw_a)                       # eager warm-up + capture of graph A
+    gen.generate(model.engine, px, **kw_b)                       # other cache length
+    gen.generate(model.engine, px, **kw_c)                       # other row count
+    model.params = p2
+    replay = gen.generate(model.engine, px, **kw_a)["sequences"].cpu().numpy()
+    eager = gen.generate(model.engine, px, use_cuda_graph=False, **kw_a)["sequences"].cpu().numpy()
+    np.testing.assert_array_equal(replay, eager)
