@@ -286,9 +286,24 @@ def bench_generate(model, cfg, peaks, dev, B=64, reps=5):
     ms = e0.elapsed_time(e1) / reps
     cps = B / (ms / 1e3)
     gbs = GEN_BYTES_PER_64 * (cps / 64) / 1e9
+    # dominant kernel of the decode loop: the persistent decoder step (one launch per generated position), timed
+    # with CUDA events around every launch of one eager (un-captured) generate() call
+    from mic_b200 import ops, generation as gen
+    ops.TIMED["mic_decoder_step"] = []
+    gen.generate(model.engine, px, use_cuda_graph=False, pad_token_id=1, eos_token_id=2, decoder_start_token_id=2,
+                 min_length=0, forced_eos_token_id=2, length_penalty=1.0, early_stopping=True, **kw)
+    torch.cuda.synchronize()
+    ev = ops.TIMED.pop("mic_decoder_step")
+    step_ms = sum(s_.elapsed_time(e_) for s_, e_ in ev) / max(1, len(ev))
+    # SURVEY 8d per decode step at B=64, beam 4: decoder weights 352.7 MB + cross K/V 157.3 MB + self K/V 402.7 MB (avg)
+    step_bytes = (352.7e6 + 157.3e6 + 402.7e6) * (B / 64.0)
+    step_gbs = step_bytes / (step_ms / 1e3) / 1e9 if step_ms > 0 else 0.0
     return {"metric": "beam4_len64_captions_per_s", "value": cps, "unit": "captions/s", "ms_per_call": ms, "batch": B,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm_gbs"]}}
+                         "frac": gbs / peaks["hbm_gbs"]},
+            "decoder_step_kernel": {"launches": len(ev), "ms_per_launch": step_ms, "bytes_per_launch": step_bytes,
+                                    "achieved": step_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": step_gbs / peaks["hbm_gbs"]}}
 
 
 def main():

@@ -109,10 +109,17 @@ class CaptionEngine:
         return (self.drop_seed, (site * 0x9E3779B9) & 0x7FFFFFFF, self.dropout_p)
 
     # ------------------------------------------------------------------------------------------
-    def _workspace(self, floats):
-        if self._ws is None or self._ws.numel() < floats:
-            self._ws = torch.empty(int(floats), dtype=F32, device=self.dev)
-        return self._ws
+    def _workspace(self, floats, side=False):
+        """fp32 scratch for the column-sum kernels (one per stream).  Outgrown workspaces stay allocated: a captured
+        graph may still replay on them."""
+        k = "_ws_side" if side else "_ws"
+        cur = getattr(self, k, None)
+        if cur is None or cur.numel() < floats:
+            if cur is not None:
+                self.__dict__.setdefault("_ws_old", []).append(cur)
+            cur = torch.empty(int(floats), dtype=F32, device=self.dev)
+            setattr(self, k, cur)
+        return cur
 
     def _ln_fwd(self, x, name, eps, out, stats=None):
         ps = self.ps
@@ -149,6 +156,8 @@ class CaptionEngine:
             ops.act_bwd_colsum(dy, u, act, du, gb, ws)
             dy = du
         elif gb is not None:
+            # (moving this plain column sum to the side stream next to the wgrad GEMM was measured: no gain, the
+            #  step is power-capped rather than stream-serialisation bound)
             ops.act_bwd_colsum(dy, None, "none", None, gb, ws)
         dyv = dy
         self._fork_side(lambda: ops.gemm(x, dyv, a_mn=True, b_mn=True, out=gw), x, dyv, gw)   # dW[K,N] = x^T dy

@@ -253,10 +253,15 @@ def colsum_workspace_floats(M, N):
     return lib().mic_colsum_workspace_floats(M, N)
 
 
-def act_bwd_colsum(dy, u, act, du, dbias, workspace, accumulate=False, dropout=None):
+def act_bwd_colsum(dy, u, act, du, dbias, workspace, accumulate=False, dropout=None, side=False):
+    """side=True: second half of the ticket counters (a launch on another stream may run concurrently with a
+    main-stream launch of the same kernel family; N <= 131072 either way)."""
     M, N = dy.shape
+    cnt = counters(dy.device)
+    if side:
+        cnt = cnt[512:]
     _call("mic_act_bwd_colsum", _p(dy), _ld(dy), _p(u), _ld(u) if u is not None else 0, ACT[act], _p(du),
-          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), _p(counters(dy.device)), M, N,
+          _ld(du) if du is not None else 0, _p(dbias), int(accumulate), _p(workspace), _p(cnt), M, N,
           *_drop(dropout))
 
 
