@@ -639,8 +639,13 @@ extern "C" int mic_decoder_step(void* stream, const void* plan_dev, int num_laye
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-  cfg.attrs = nullptr;
-  cfg.numAttrs = 0;
+  // cooperative launch: the driver guarantees (or refuses) co-residency of the whole grid, which the grid barrier
+  // needs; works under stream capture (kernel node attribute)
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
   MIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decoder_step_kernel, a));
   return MIC_OK;
 }
