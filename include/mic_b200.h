@@ -81,9 +81,12 @@ int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, const void* 
  * running top-8 for its rows across all of its vocabulary tiles; partial arrays are
  * [mic_lm_head_search_num_partials(M), M(, 8)] */
 int mic_lm_head_search_num_partials(int M);
+/* upper_val / upper_idx (optional, [M]): second pass for 5..8 beams - only (logit, token) pairs ranking strictly
+ * after the row's pair are considered (pass the 8th best of the first pass, mic_search_merge last_val/last_idx);
+ * the partial statistics of such a pass are meaningless. */
 int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
                        const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
-                       float* cand_val, int* cand_idx);
+                       float* cand_val, int* cand_idx, const float* upper_val, const int* upper_idx);
 
 /* packed-operand variant of mic_lm_head_search: H and E are given as K-major tile images (mic_pack_kmajor_tiles:
  * H with tile_rows = 128 - the persistent decoder step writes it directly -, E with tile_rows = 256), so that a
@@ -93,7 +96,7 @@ long long mic_pack_kmajor_tiles_bytes(long long rows, int K, int tile_rows);
 int mic_pack_kmajor_tiles(void* stream, const void* src, long long ld, long long rows, int K, int tile_rows, void* out);
 int mic_lm_head_search_packed(void* stream, const void* h_tiles, const void* e_tiles, const float* bias,
                               int mask_token, int M, int V, int K, float* pmax, float* psum, float* cand_val,
-                              int* cand_idx);
+                              int* cand_idx, const float* upper_val, const int* upper_idx);
 
 /* ---- normalisation / embedding / elementwise (HBM-bound, vectorised, warp-shuffle reductions) ----
  * flax.linen.LayerNorm (fp32 statistics, var = E[x^2]-E[x]^2) as used by FlaxCLIPEncoderLayer,
@@ -218,14 +221,18 @@ int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, 
                      unsigned long long* phase_times);
 
 /* ---- search steps (generation_clip_vision_utils.py) ---------------------------------------------------
- * merge the lm_head_search slab partials: per row log-softmax normaliser + top-8 (log-prob, token) */
+ * merge the lm_head_search slab partials: per row log-softmax normaliser + top-8 (log-prob, token),
+ * written to row_lp / row_tok [R, ld_out] at columns col_off .. col_off+7.  lse_given = 1: second pass (ranks
+ * 9..16, 5..8 beams) - the normaliser is READ from row_max_logsum (written by the first pass).  last_val / last_idx
+ * (optional, [R]): raw logit and token of the 8th best = the upper bound handed to the second search pass. */
 int mic_search_merge(void* stream, const float* pmax, const float* psum, const float* cand_val, const int* cand_idx,
-                     int num_partials, int R, float* row_lp, int* row_tok, float* row_max_logsum);
+                     int num_partials, int R, float* row_lp, int* row_tok, float* row_max_logsum, int ld_out,
+                     int col_off, int lse_given, float* last_val, int* last_idx);
 /* beam_search_body_fn :822-966 steps 2-8 [G5]; forced_token >= 0 applies ForcedBOS/ForcedEOS [G2] */
 int mic_beam_step(void* stream, const float* row_lp, const int* row_tok, int forced_token, int B, int K, int L,
                   int V, int cur_len, int eos_token_id, int early_stopping, float length_penalty, int* running_seq,
                   float* running_scores, int* sequences, float* scores, int* finished, int* ancestors,
-                  int* next_token, int* active);
+                  int* next_token, int* active, int cand_per_row);   /* row_lp/row_tok are [B*K, cand_per_row]: 8 (K <= 4) or 16 (K <= 8) */
 /* beam_search_cond_fn :798-820 [G6] for the next iteration; writes *active */
 int mic_beam_cond(void* stream, const float* running_scores, const float* scores, const int* finished, int B, int K,
                   int cur_len, int max_length, float length_penalty, int early_stopping, int* active);

@@ -32,10 +32,10 @@ SIGNATURES = {
     "mic_ce_finalize": [P, P, P, P, P, P, I, I, I, F, P, P, P, P],
     "mic_lm_head_ce_grad": [P, P, L, P, L, P, P, P, P, F, F, I, I, I, P, L],
     "mic_lm_head_search_num_partials": [I],
-    "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P],
+    "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P, P, P],
     "mic_pack_kmajor_tiles_bytes": [L, I, I],
     "mic_pack_kmajor_tiles": [P, P, L, L, I, I, P],
-    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P],
+    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
     "mic_layernorm_fwd": [P, P, P, P, F, P, P, P, I, I],
     "mic_residual_ln_fwd": [P, P, P, P, P, P, F, P, I, I],
     "mic_layernorm_bwd_workspace_floats": [I, I],
@@ -53,8 +53,8 @@ SIGNATURES = {
     "mic_attention_fwd": [P, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, F],
     "mic_attention_bwd": [P, P, L, P, L, P, L, P, L, P, L, P, P, I, P, L, P, L, P, L, I, I, I, I, I, F],
     "mic_decode_attention": [P, P, L, P, P, L, P, I, I, I, P, L, I, I, I, F],
-    "mic_search_merge": [P, P, P, P, P, I, I, P, P, P],
-    "mic_beam_step": [P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P, P],
+    "mic_search_merge": [P, P, P, P, P, I, I, P, P, P, I, I, I, P, P],
+    "mic_beam_step": [P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P, P, P, P, P, I],
     "mic_beam_cond": [P, P, P, P, I, I, I, I, F, I, P],
     "mic_beam_finalize": [P, P, P, P, P, P, I, I, I, P, P],
     "mic_greedy_step": [P, P, I, I, I, I, I, I, P, P, P, P],

@@ -9,7 +9,8 @@
 namespace {
 
 constexpr int TOPK = 8;          // == micgemm::SEARCH_TOPK
-constexpr int MAX_BEAMS = 4;     // candidates kept = 2 * beams <= TOPK
+constexpr int MAX_BEAMS = 8;     // candidates kept per image = 2 * beams <= MAX_CAND
+constexpr int MAX_CAND = 16;     // per-row candidate list length: 8 (beams <= 4) or 16 (two search passes, beams 5..8)
 #define NEG_BIG (-1.0e7f)
 
 __device__ __forceinline__ bool better(float v, int i, float v2, int i2) {   // (value desc, index asc)
@@ -25,7 +26,8 @@ __device__ __forceinline__ bool better(float v, int i, float v2, int i2) {   // 
 __global__ void __launch_bounds__(128)
 search_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, const float* __restrict__ cval,
                     const int* __restrict__ cidx, int nparts, int R, float* __restrict__ row_lp,
-                    int* __restrict__ row_tok, float* __restrict__ row_max_lse) {
+                    int* __restrict__ row_tok, float* __restrict__ row_max_lse, int ld_out, int col_off, int lse_given,
+                    float* __restrict__ last_val, int* __restrict__ last_idx) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -74,8 +76,11 @@ search_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ ps
     }
   }
   sm = warp_sum(sm);
-  const float logsum = logf(sm);
-  if (lane == 0 && row_max_lse) {
+  float logsum = logf(sm);
+  if (lse_given) {            // second search pass (ranks 9..16): the softmax statistics are those of the first pass
+    mx = row_max_lse[2 * r];
+    logsum = row_max_lse[2 * r + 1];
+  } else if (lane == 0 && row_max_lse) {
     row_max_lse[2 * r] = mx;
     row_max_lse[2 * r + 1] = logsum;
   }
@@ -96,8 +101,12 @@ search_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ ps
       }
     }
     if (lane == 0) {
-      row_lp[(long long)r * TOPK + k] = (bv - mx) - logsum;
-      row_tok[(long long)r * TOPK + k] = bi;
+      row_lp[(long long)r * ld_out + col_off + k] = (bv - mx) - logsum;
+      row_tok[(long long)r * ld_out + col_off + k] = bi;
+      if (k == TOPK - 1 && last_val) {      // raw (logit, token) of the 8th best: upper bound of the next pass
+        last_val[r] = bv;
+        last_idx[r] = bi;
+      }
     }
     if (lane == bl) {
 #pragma unroll
@@ -134,9 +143,10 @@ __device__ __forceinline__ int warp_best(float v, int key, bool valid, int lane)
 // Beam step: one warp per image.  State arrays follow the reference's BeamSearchState.
 // ---------------------------------------------------------------------------------------------
 struct BeamArgs {
-  const float* row_lp;     // [B*K, 8] log-probs of each beam-row's best tokens (unused when forced >= 0)
-  const int* row_tok;      // [B*K, 8]
+  const float* row_lp;     // [B*K, cpr] log-probs of each beam-row's best tokens (unused when forced >= 0)
+  const int* row_tok;      // [B*K, cpr]
   int forced_token;        // >= 0: ForcedBOS/ForcedEOS step (scores: -inf everywhere, 0 at this id)
+  int cpr;                 // candidates per row in row_lp / row_tok (8 or 16), >= 2K
   int B, K, L, V;
   int cur_len;
   int eos, early_stopping;
@@ -162,8 +172,8 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const BeamArgs a) {
   int* old_run = sh;                    // [K, L]
   int* old_seq = sh + K * L;            // [K, L]
   int* old_anc = sh + 2 * K * L;        // [K, L]
-  __shared__ float s_tlp[TOPK], s_tlp2[MAX_BEAMS + TOPK], s_newscore[MAX_BEAMS], s_newrun[MAX_BEAMS];
-  __shared__ int s_beam[TOPK], s_tok[TOPK], s_fin[TOPK], s_runsel[MAX_BEAMS], s_mergesel[MAX_BEAMS], s_newfin[MAX_BEAMS];
+  __shared__ float s_tlp[MAX_CAND], s_tlp2[MAX_BEAMS + MAX_CAND], s_newscore[MAX_BEAMS], s_newrun[MAX_BEAMS];
+  __shared__ int s_beam[MAX_CAND], s_tok[MAX_CAND], s_fin[MAX_CAND], s_runsel[MAX_BEAMS], s_mergesel[MAX_BEAMS], s_newfin[MAX_BEAMS];
   for (int i = lane; i < K * L; i += 32) {
     old_run[i] = a.running_seq[(long long)b * K * L + i];
     old_seq[i] = a.sequences[(long long)b * K * L + i];
@@ -175,36 +185,62 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const BeamArgs a) {
   // local-memory candidate arrays cost 36 us per step)
   {
     // ---- 3. top 2K over the K*V candidates (value desc, flat index asc) ----
-    float cv = -INFINITY;
-    int cflat = 0x7fffffff;
-    bool valid = false;
-    if (a.forced_token >= 0) {
-      if (lane < K) {                                   // the forced id of every beam: log-prob 0
-        cv = 0.0f + a.running_scores[b * K + lane];
-        cflat = lane * a.V + a.forced_token;
-        valid = true;
-      } else if (lane < 3 * K) {                        // -inf fillers: lowest flat indices other than the forced id
-        int f = lane - K;
-        if (f >= a.forced_token) ++f;
-        if (f < a.V) {
-          cflat = f;
-          valid = true;
+    // up to K * cpr = 128 candidates: 4 slots per lane
+    constexpr int SLOTS = MAX_BEAMS * MAX_CAND / 32;
+    float cv[SLOTS];
+    int cflat[SLOTS];
+    bool valid[SLOTS];
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      cv[q] = -INFINITY;
+      cflat[q] = 0x7fffffff;
+      valid[q] = false;
+      const int i = lane + 32 * q;
+      if (a.forced_token >= 0) {
+        if (i < K) {                                      // the forced id of every beam: log-prob 0
+          cv[q] = 0.0f + a.running_scores[b * K + i];
+          cflat[q] = i * a.V + a.forced_token;
+          valid[q] = true;
+        } else if (i < 3 * K) {                           // -inf fillers: lowest flat indices other than the forced id
+          int f = i - K;
+          if (f >= a.forced_token) ++f;
+          if (f < a.V) {
+            cflat[q] = f;
+            valid[q] = true;
+          }
         }
+      } else if (i < K * a.cpr) {
+        const int k = i / a.cpr;
+        cv[q] = a.row_lp[(long long)b * K * a.cpr + i] + a.running_scores[b * K + k];
+        cflat[q] = k * a.V + a.row_tok[(long long)b * K * a.cpr + i];
+        valid[q] = true;
       }
-    } else if (lane < K * TOPK) {
-      const int k = lane / TOPK;
-      cv = a.row_lp[(long long)b * K * TOPK + lane] + a.running_scores[b * K + k];
-      cflat = k * a.V + a.row_tok[(long long)b * K * TOPK + lane];
-      valid = true;
     }
     // lane j (< 2K) ends up holding candidate j of the ordered top-2K list
     float my_tlp = 0.f;
     int my_flat = 0;
     for (int j = 0; j < K2; ++j) {
-      const int w = warp_best(cv, cflat, valid, lane);
-      const float wv = __shfl_sync(0xffffffffu, cv, w);
-      const int wf = __shfl_sync(0xffffffffu, cflat, w);
-      if (lane == w) valid = false;
+      // the lane's own best slot, then the warp's best lane
+      float lv = cv[0];
+      int lf = cflat[0], ls = 0;
+      bool lvalid = valid[0];
+#pragma unroll
+      for (int q = 1; q < SLOTS; ++q) {
+        if (valid[q] && (!lvalid || better(cv[q], cflat[q], lv, lf))) {
+          lv = cv[q];
+          lf = cflat[q];
+          ls = q;
+          lvalid = true;
+        }
+      }
+      const int w = warp_best(lv, lf, lvalid, lane);
+      const float wv = __shfl_sync(0xffffffffu, lv, w);
+      const int wf = __shfl_sync(0xffffffffu, lf, w);
+      if (lane == w) {
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q)
+          if (q == ls) valid[q] = false;
+      }
       if (lane == j) {
         my_tlp = wv;
         my_flat = wf;
@@ -381,20 +417,27 @@ __global__ void greedy_cond_kernel(const int* __restrict__ finished, int R, int 
 
 extern "C" int mic_search_merge(void* stream, const float* pmax, const float* psum, const float* cand_val,
                                 const int* cand_idx, int num_partials, int R, float* row_lp, int* row_tok,
-                                float* row_max_logsum) {
-  MIC_CHECK_CUDA(mic_launch(search_merge_kernel, dim3((R + 3) / 4), dim3(128), 0, STREAM, pmax, psum, cand_val, cand_idx, num_partials, R, row_lp,
-                                                       row_tok, row_max_logsum));
+                                float* row_max_logsum, int ld_out, int col_off, int lse_given, float* last_val,
+                                int* last_idx) {
+  MIC_CHECK_ARG(ld_out >= TOPK && col_off >= 0 && col_off + TOPK <= ld_out, "search_merge: ld_out=%d col_off=%d", ld_out,
+                col_off);
+  MIC_CHECK_ARG(!lse_given || row_max_logsum, "search_merge: lse_given needs row_max_logsum");
+  MIC_CHECK_CUDA(mic_launch(search_merge_kernel, dim3((R + 3) / 4), dim3(128), 0, STREAM, pmax, psum, cand_val, cand_idx,
+                            num_partials, R, row_lp, row_tok, row_max_logsum, ld_out, col_off, lse_given, last_val,
+                            last_idx));
   return MIC_OK;
 }
 
 extern "C" int mic_beam_step(void* stream, const float* row_lp, const int* row_tok, int forced_token, int B, int K,
                              int L, int V, int cur_len, int eos_token_id, int early_stopping, float length_penalty,
                              int* running_seq, float* running_scores, int* sequences, float* scores, int* finished,
-                             int* ancestors, int* next_token, int* active) {
+                             int* ancestors, int* next_token, int* active, int cand_per_row) {
   MIC_CHECK_ARG(K >= 1 && K <= MAX_BEAMS, "beam_step: num_beams=%d must be in [1,%d]", K, MAX_BEAMS);
+  MIC_CHECK_ARG((cand_per_row == TOPK || cand_per_row == MAX_CAND) && cand_per_row >= 2 * K,
+                "beam_step: cand_per_row=%d must be 8 or 16 and >= 2*num_beams", cand_per_row);
   MIC_CHECK_ARG(cur_len >= 1 && cur_len < L, "beam_step: cur_len=%d out of range for max_length=%d", cur_len, L);
   BeamArgs a;
-  a.row_lp = row_lp; a.row_tok = row_tok; a.forced_token = forced_token;
+  a.row_lp = row_lp; a.row_tok = row_tok; a.forced_token = forced_token; a.cpr = cand_per_row;
   a.B = B; a.K = K; a.L = L; a.V = V; a.cur_len = cur_len; a.eos = eos_token_id;
   a.early_stopping = early_stopping; a.length_penalty = length_penalty;
   a.running_seq = running_seq; a.running_scores = running_scores; a.sequences = sequences; a.scores = scores;

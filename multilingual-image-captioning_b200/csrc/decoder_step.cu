@@ -399,7 +399,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           const int gw = ew * G + cta, nw = G * EW;      // consecutive items land on different SMs
           DecAttnArgs a = ph.attn;
           if (ph.keys_from_pos) a.n_keys = args.pos + 1;
-          // host guarantees n_keys <= 64 and rows_per_kv <= 4 (mic_decoder_plan_init)
+          // host guarantees n_keys <= 64 and rows_per_kv <= 8 (mic_decoder_plan_init): the item's query rows sit in
+          // rows 0..7 of the MMA tile
           const int items = ((a.R + a.rows_per_kv - 1) / a.rows_per_kv) * a.H;
 #pragma unroll 1
           const bool tra = args.prof && cta == TRACE_CTA && ew == 0 && p == 1 + 1 + 11 * 5;
@@ -515,8 +516,8 @@ extern "C" int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_dec
   MIC_CHECK_ARG(d_model % 64 == 0 && d_model <= 1024 && ffn_dim % 64 == 0 && d_model == heads * HD,
                 "decoder plan: d_model=%d heads=%d ffn=%d unsupported (head_dim 64, d_model <= 1024)", d_model, heads,
                 ffn_dim);
-  MIC_CHECK_ARG(cache_len <= 64 && enc_tokens <= 64 && rows_per_image >= 1 && rows_per_image <= 4 && R > 0,
-                "decoder plan: cache_len=%d / enc_tokens=%d must be <= 64 and rows_per_image=%d in 1..4", cache_len,
+  MIC_CHECK_ARG(cache_len <= 64 && enc_tokens <= 64 && rows_per_image >= 1 && rows_per_image <= 8 && R > 0,
+                "decoder plan: cache_len=%d / enc_tokens=%d must be <= 64 and rows_per_image=%d in 1..8", cache_len,
                 enc_tokens, rows_per_image);
   MIC_CHECK_ARG(act == MIC_ACT_GELU || act == MIC_ACT_NONE, "decoder plan: activation %d not supported (gelu only)", act);
   MIC_CHECK_ARG((reinterpret_cast<uintptr_t>(plan_dev) & 127) == 0, "decoder plan buffer must be 128-byte aligned");

@@ -478,6 +478,10 @@ struct EpiSearchParams {
   // [row tile][k block], fetched with one bulk copy per operand per stage instead of 384 TMA box rows
   const bf16* a_tiles;
   const bf16* b_tiles;
+  // second pass for 5..8 beams (2K = 10..16 candidates per row): only (logit, token) pairs that rank strictly after
+  // the row's pair (upper_val, upper_idx) - the 8th best of the first pass - are considered; null = first pass
+  const float* upper_val;
+  const int* upper_idx;
 };
 
 // The launcher sizes the grid as a multiple of num_m_blocks with group_m == num_m_blocks, so every CTA
@@ -491,6 +495,8 @@ struct EpiSearch {
     float mx, sm;
     float tv[SEARCH_TOPK];
     int ti[SEARCH_TOPK];
+    float uv;
+    int ui;
   };
   __device__ static void kernel_begin(const Params&, State& st) {
     st.mx = -INFINITY;
@@ -501,7 +507,12 @@ struct EpiSearch {
       st.ti[i] = 0x7fffffff;
     }
   }
-  __device__ static void tile_begin(const Params&, State&, const Shape&, int, int, int) {}
+  __device__ static void tile_begin(const Params& p, State& st, const Shape& s, int row, int, int) {
+    if (p.upper_val) {
+      st.uv = row < s.M ? p.upper_val[row] : -INFINITY;
+      st.ui = row < s.M ? p.upper_idx[row] : 0;
+    }
+  }
   __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
   __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
     if (col0 >= s.N) return;
@@ -526,6 +537,11 @@ struct EpiSearch {
     if (mrel < 64u) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = (mrel == static_cast<unsigned>(j)) ? -INFINITY : v[j];
+    }
+    if (p.upper_val) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (!(v[j] < st.uv || (v[j] == st.uv && col0 + j > st.ui))) v[j] = -INFINITY;
     }
     float cmax = v[0];
 #pragma unroll

@@ -176,13 +176,14 @@ def decode_step_fused(engine, cache: DecodeCache, tokens, pos: int, fp=None):
     return fp["bufs"]["h_out_tiles"] if fp["bufs"]["h_out_tiles"] is not None else fp["bufs"]["h_out"]
 
 
-def _search_ws(engine, R):
+def _search_ws(engine, R, cand_per_row=8):
     b, V = engine.bufs, engine.t.vocab_size
     n = ops.lm_head_search_num_partials(R)
     return {"nparts": n, "pmax": b.get("gen.pmax", (n, R), F32), "psum": b.get("gen.psum", (n, R), F32),
             "cand_val": b.get("gen.cand_val", (n, R, 8), F32), "cand_idx": b.get("gen.cand_idx", (n, R, 8), I32),
-            "row_lp": b.get("gen.row_lp", (R, 8), F32), "row_tok": b.get("gen.row_tok", (R, 8), I32),
-            "row_ml": b.get("gen.row_ml", (R, 2), F32)}
+            "row_lp": b.get("gen.row_lp", (R, cand_per_row), F32), "row_tok": b.get("gen.row_tok", (R, cand_per_row), I32),
+            "row_ml": b.get("gen.row_ml", (R, 2), F32),
+            "last_val": b.get("gen.last_val", (R,), F32), "last_idx": b.get("gen.last_idx", (R,), I32)}
 
 
 def _forced_token(cur_len, max_length, forced_bos, forced_eos):
@@ -202,12 +203,18 @@ def _step(engine, cache, tokens, pos):
 
 
 def _lm_head_search(engine, cache, hf, mask_token, ws):
+    """lm_head + log-softmax partials + per-row candidates.  8 candidates per row cover 2*num_beams for <= 4 beams;
+    5..8 beams run the search a second time restricted to what ranks after the first pass's 8th (exact: both passes
+    compute bit-identical logits)."""
     ps, t = engine.ps, engine.t
-    if cache.fused is not None and "e_tiles" in cache.fused:
-        ops.lm_head_search_packed(hf, cache.fused["e_tiles"], ps.f("flb"), int(mask_token), cache.rows, t.vocab_size,
-                                  t.d_model, ws)
-    else:
-        ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws)
+    passes = 2 if ws["row_lp"].shape[1] > 8 else 1
+    for i in range(passes):
+        if cache.fused is not None and "e_tiles" in cache.fused:
+            ops.lm_head_search_packed(hf, cache.fused["e_tiles"], ps.f("flb"), int(mask_token), cache.rows, t.vocab_size,
+                                      t.d_model, ws, second_pass=i == 1)
+        else:
+            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws, second_pass=i == 1)
+        ops.search_merge(ws, cache.rows, second_pass=i == 1)
 
 
 def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams, min_length,
@@ -224,12 +231,12 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
     cache = DecodeCache(engine, R, Lmax, enc_kv, K, use_ancestors=K > 1)
     # the persistent decoder-step kernel stages <= 64 keys per attention item and <= 4 beams per image; longer
     # searches (the model default max_length is 200) take the per-op path
-    fused_ok = (Lmax <= 64 and engine.c.num_tokens <= 64 and K <= 4 and t.pre_layernorm and t.final_layer_norm
+    fused_ok = (Lmax <= 64 and engine.c.num_tokens <= 64 and K <= 8 and t.pre_layernorm and t.final_layer_norm
                 and t.activation_function == "gelu" and t.decoder_layers <= 12)
     import os
     if getattr(engine, "fused_decoder", True) and fused_ok and os.environ.get("MIC_FUSED_DECODER", "1") != "0":
         cache.fused = fused_prepare(engine, cache, packed_search=os.environ.get("MIC_PACKED_SEARCH", "1") != "0")
-    ws = _search_ws(engine, R)
+    ws = _search_ws(engine, R, 8 if K <= 4 else 16)
     active = torch.ones(1, dtype=I32, device=dev)
     next_token = torch.full((R,), decoder_start_token_id, dtype=I32, device=dev)
     mask_eos = min_length is not None and eos_token_id is not None and min_length > -1
@@ -246,7 +253,6 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
             if forced < 0:
                 mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
                 _lm_head_search(engine, cache, hf, mt, ws)
-                ops.search_merge(ws, R)
             ops.greedy_step(ws, st, forced, R, Lmax, cur_len, eos_token_id, pad_token_id)
             ops.greedy_cond(st, R, cur_len + 1, Lmax)
         return {"sequences": st["sequences"]}
@@ -267,7 +273,6 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
         if forced < 0:
             mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
             _lm_head_search(engine, cache, hf, mt, ws)
-            ops.search_merge(ws, R)
         ops.beam_step(ws, st, forced, B, K, Lmax, V, cur_len, eos_token_id, early_stopping, length_penalty)
         ops.beam_cond(st, B, K, cur_len + 1, Lmax, length_penalty, early_stopping)
     out_seq = torch.empty((B, Lmax), dtype=I32, device=dev)
@@ -281,8 +286,8 @@ def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_w
     """`generate` :128-336.  encode() truncates pixels to int32 first (modeling_clip_vision_mbart.py:330).
     The first call for a given (batch, search settings) runs eagerly (allocates every buffer); the whole
     loop is then captured into ONE CUDA graph and later calls only copy the pixels in and replay it."""
-    if kw["num_beams"] > 4:
-        raise NotImplementedError("beam-step kernel keeps 2*num_beams <= 8 candidates (num_beams <= 4)")
+    if kw["num_beams"] > 8:
+        raise NotImplementedError("beam search keeps 2*num_beams <= 16 candidates per image row (num_beams <= 8)")
     px = pixel_values.to(engine.dev, F32).contiguous()
     # parameters are frozen while the loop runs: GEMMs prefetch weight tiles ahead of their dependency wait
     prefetch_weights = pdl if prefetch_weights is None else prefetch_weights

@@ -104,9 +104,10 @@ def pack_kmajor_tiles(src, tile_rows, out):
     _call("mic_pack_kmajor_tiles", _p(src), _ld(src), rows, K, tile_rows, _p(out))
 
 
-def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws):
+def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws, second_pass=False):
     _call("mic_lm_head_search_packed", _p(h_tiles), _p(e_tiles), _p(bias), mask_token, M, V, K, _p(ws["pmax"]),
-          _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]))
+          _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]), _p(ws["last_val"]) if second_pass else None,
+          _p(ws["last_idx"]) if second_pass else None)
 
 
 def lm_head_ce_stats(h, emb, bias, labels, ws, logits_out=None):
@@ -140,16 +141,21 @@ def lm_head_ce_grad(h, emb, bias, labels, ws, conf, low, dlogits):
           _p(ws["row_w"]), float(conf), float(low), M, V, K, _p(dlogits), _ld(dlogits))
 
 
-def lm_head_search(h, emb, bias, mask_token, ws):
+def lm_head_search(h, emb, bias, mask_token, ws, second_pass=False):
     M, K = h.shape
     V = emb.shape[0]
     _call("mic_lm_head_search", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), int(mask_token), M, V, K,
-          _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]))
+          _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]),
+          _p(ws["last_val"]) if second_pass else None, _p(ws["last_idx"]) if second_pass else None)
 
 
-def search_merge(ws, R):
+def search_merge(ws, R, second_pass=False):
+    """Top-8 per row of the slab partials -> ws["row_lp"/"row_tok"] [R, cpr] (cpr = 8, or 16 for 5..8 beams: the
+    second pass fills columns 8..15 with the normaliser of the first)."""
+    cpr = ws["row_lp"].shape[1]
     _call("mic_search_merge", _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]), ws["nparts"],
-          R, _p(ws["row_lp"]), _p(ws["row_tok"]), _p(ws["row_ml"]))
+          R, _p(ws["row_lp"]), _p(ws["row_tok"]), _p(ws["row_ml"]), cpr, 8 if second_pass else 0, int(second_pass),
+          _p(ws.get("last_val")), _p(ws.get("last_idx")))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -339,7 +345,7 @@ def beam_step(ws, st, forced_token, B, K, L, V, cur_len, eos, early_stopping, le
     _call("mic_beam_step", _p(ws["row_lp"]), _p(ws["row_tok"]), int(forced_token), B, K, L, V, cur_len, eos,
           int(early_stopping), float(length_penalty), _p(st["running_seq"]), _p(st["running_scores"]),
           _p(st["sequences"]), _p(st["scores"]), _p(st["finished"]), _p(st["ancestors"]), _p(st["next_token"]),
-          _p(st["active"]))
+          _p(st["active"]), ws["row_lp"].shape[1])
 
 
 def beam_cond(st, B, K, cur_len, max_length, length_penalty, early_stopping):

@@ -47,7 +47,8 @@ def cuda_beam_search(logits_fn, B, K, L, *, eos=2, pad=1, start=2, forced_bos=No
           "active": torch.ones(1, dtype=I32, device=dev)}
     st["running_seq"][:, :, 0] = start
     st["running_scores"][:, 0] = 0.0
-    ws = {"row_lp": torch.empty((R, 8), dtype=F32, device=dev), "row_tok": torch.empty((R, 8), dtype=I32, device=dev)}
+    cpr = 8 if K <= 4 else 16                     # candidates per row handed to the beam step (>= 2K)
+    ws = {"row_lp": torch.empty((R, cpr), dtype=F32, device=dev), "row_tok": torch.empty((R, cpr), dtype=I32, device=dev)}
     anc_log = []
     for cur_len in range(1, L):
         forced = -1
@@ -60,7 +61,7 @@ def cuda_beam_search(logits_fn, B, K, L, *, eos=2, pad=1, start=2, forced_bos=No
             lp = rg.log_softmax(logits_fn(cur_len, seqs))
             if min_length is not None and min_length > -1 and cur_len < min_length:
                 lp[:, eos] = -np.inf
-            val, idx = rg.top_k(lp, 8)
+            val, idx = rg.top_k(lp, cpr)
             ws["row_lp"].copy_(torch.from_numpy(val))
             ws["row_tok"].copy_(torch.from_numpy(idx.astype(np.int32)))
         ops.beam_step(ws, st, forced, B, K, L, V, cur_len, eos, early_stopping, length_penalty)
@@ -79,7 +80,7 @@ class _Cfg:
         decoder_layers = 1
 
 
-@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 8])
 @pytest.mark.parametrize("L", [3, 7, 16])
 @pytest.mark.parametrize("eos_boost", [0.0, 3.0, 6.0])
 @pytest.mark.parametrize("variant", ["plain", "ties", "no_forced_bos", "lp2", "no_early", "minlen"])

@@ -103,6 +103,44 @@ def test_greedy_edge_cases(eos_bias):
                 assert seq[b, pos] == ref["sequences"][b, pos], (kw, eos_bias, b, pos, seq[b], ref["sequences"][b])
 
 
+@pytest.mark.parametrize("K", [5, 8])
+def test_wide_beams_two_pass_search(K):
+    """5..8 beams (the model config's default is 5): 2K > 8 candidates per row come from two search passes.  The
+    step-1 invariant (ForcedBOS) and the oracle's first real decision must be reproduced; the two-pass candidate
+    list must equal the top-16 of a direct fp32 log-softmax of our own logits."""
+    import torch
+    from mic_b200 import ops, generation as gen
+    cfg, params, batch, model = _setup(0.0)
+    ref = rg.generate(params, batch["pixel_values"], cfg, num_beams=K, max_length=8, forced_bos_token_id=1001)
+    out = model.generate(batch["pixel_values"], num_beams=K, max_length=8, forced_bos_token_id=1001)
+    seq = out.sequences.cpu().numpy()
+    assert seq.shape == ref["sequences"].shape
+    assert np.all(seq[:, :2] == ref["sequences"][:, :2])
+    assert np.all(seq[:, -1] == 2) or np.all((seq[:, -1] == 2) | (seq[:, -1] == 1))
+    # candidate lists: two passes == top-16
+    eng = model.engine
+    R = 10
+    h = (torch.randn(R, cfg.mbart_config.d_model, device="cuda") * 0.5).to(torch.bfloat16)
+    ws = gen._search_ws(eng, R, 16)
+    emb, flb = eng.ps.w("shared"), eng.ps.f("flb")
+    for i in range(2):
+        ops.lm_head_search(h, emb, flb, -1, ws, second_pass=i == 1)
+        ops.search_merge(ws, R, second_pass=i == 1)
+    logits = h.float() @ emb.float().t() + flb.reshape(1, -1).float()
+    lp = torch.log_softmax(logits, dim=-1)
+    val, idx = torch.sort(lp, dim=-1, descending=True, stable=True)
+    got_tok = ws["row_tok"].cpu().numpy()
+    got_lp = ws["row_lp"].cpu().numpy()
+    assert np.all(np.diff(got_lp, axis=1) <= 1e-6)                       # one descending list of 16
+    for r in range(R):
+        assert len(set(got_tok[r].tolist())) == 16
+        # same SET as the fp32 top-16 up to near-ties at the boundary
+        margin = float(val[r, 15] - val[r, 16])
+        if margin > 1e-3:
+            assert set(got_tok[r].tolist()) == set(idx[r, :16].cpu().numpy().tolist()), r
+    np.testing.assert_allclose(got_lp, np.take_along_axis(lp.cpu().numpy(), got_tok.astype(np.int64), axis=1), atol=2e-3)
+
+
 def test_batch_of_one_and_odd_sizes():
     cfg, params, batch, model = _setup(0.0)
     for B in (1, 3):
