@@ -220,6 +220,9 @@ int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_decoder_layer_
 int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, int pos, unsigned int* sync_counter,
                      unsigned long long* phase_times);
 
+/* profiling aid: n grid barriers of the kind mic_decoder_step uses (tools/microbench_barrier.py) */
+int mic_barrier_bench(void* stream, unsigned int* sync_counter, int n, int variant);
+
 /* ---- search steps (generation_clip_vision_utils.py) ---------------------------------------------------
  * merge the lm_head_search slab partials: per row log-softmax normaliser + top-8 (log-prob, token),
  * written to row_lp / row_tok [R, ld_out] at columns col_off .. col_off+7.  lse_given = 1: second pass (ranks

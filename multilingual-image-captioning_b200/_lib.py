@@ -24,6 +24,7 @@ SIGNATURES = {
     "mic_decoder_pack_weights": [P, P, I, I, I, P],
     "mic_decoder_plan_init": [P, P, P, I, P, P, I, I, I, I, I, I, I, L, I, F],
     "mic_decoder_step": [P, P, I, I, I, P, P],
+    "mic_barrier_bench": [P, P, I, I],
     "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I, P, I, F],
     "mic_lm_head_num_partials": [I],
     "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P, P, L],

@@ -446,6 +446,35 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
   }
 }
 
+// ---- grid-barrier microbenchmark (tools/microbench_barrier.py): n barriers of the kind the step kernel uses,
+// ---- variant 0 = as used (atom.add.release + relaxed polling with nanosleep(20) + one acquire fence),
+// ---- 1 = polling without sleep, 2 = every thread fences before the CTA barrier, 3 = 256 pollers per CTA
+__global__ void __launch_bounds__(THREADS, 1) barrier_bench_kernel(unsigned int* sync, int n, int variant) {
+  const int G = gridDim.x;
+  if (threadIdx.x < 128) return;
+  const bool leader = threadIdx.x == 128;
+  for (int p = 0; p < n; ++p) {
+    if (p > 0) {
+      if (leader || variant == 3) {
+        while ((int)(ld_relaxed_gpu(sync) / (unsigned int)G) < p) {
+          if (variant != 1) __nanosleep(20);
+        }
+        fence_acquire_gpu();
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+    }
+    if (variant == 2) __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+    if (leader) {
+      const unsigned int old = atom_add_release_gpu(sync, 1u);
+      if (p == n - 1 && old == (unsigned int)n * (unsigned int)G - 1u) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(sync) = 0u;
+      }
+    }
+  }
+}
+
 // ---- weight re-pack: Flax kernel W[K, N] (row-major, pitch ld) -> tiles [n tile][k block] of 8 KB, each the
 // ---- SWIZZLE_128B image of a [64 k rows x 64 n] MN-major operand (k row kk at kk*128 B, chunk c at c ^ (kk & 7))
 struct PackJob {
@@ -648,5 +677,11 @@ extern "C" int mic_decoder_step(void* stream, const void* plan_dev, int num_laye
   cfg.attrs = at;
   cfg.numAttrs = 1;
   MIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decoder_step_kernel, a));
+  return MIC_OK;
+}
+
+extern "C" int mic_barrier_bench(void* stream, unsigned int* sync_counter, int n, int variant) {
+  barrier_bench_kernel<<<mic_num_sms(), THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sync_counter, n, variant);
+  MIC_CHECK_LAUNCH();
   return MIC_OK;
 }
