@@ -26,7 +26,7 @@ def _run(engine, fused, enc_kv, R, T, K, tokens, anc_tables):
     return torch.stack(outs), kv
 
 
-@pytest.mark.parametrize("B,K", [(6, 4), (40, 4), (3, 1)])
+@pytest.mark.parametrize("B,K", [(6, 4), (40, 4), (3, 1), (1, 1), (80, 4), (13, 8)])
 def test_fused_decoder_matches_per_op_path(B, K):
     cfg = mic_b200.tiny_config()
     model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, seed=3)
