@@ -220,6 +220,26 @@ int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_decoder_layer_
 int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, int pos, unsigned int* sync_counter,
                      unsigned long long* phase_times);
 
+/* ---- fp32 verification path (fp32 storage, fp32 SIMT arithmetic; forward + loss only) ------------------------
+ * For the parity bar of BASELINE configs[0] (B = 8, fp32: logits within 1e-3 relative, loss within 1e-4 of the
+ * reference restatement).  Row-major fp32 everywhere; B of the GEMM is [K, N] (Flax kernel, b_is_nk = 0) or
+ * [N, K] (the embedding table used as tied lm_head, b_is_nk = 1).  Small shapes only. */
+int mic_f32_gemm(void* stream, const float* A, long long lda, const float* B, long long ldb, int b_is_nk, int M, int N,
+                 int K, const float* bias, int act, const float* residual, long long ldr, float* D, long long ldd);
+int mic_f32_layernorm(void* stream, const float* x, const float* gamma, const float* beta, float eps, float* y, int M,
+                      int d);
+int mic_f32_attention(void* stream, const float* Q, long long ldq, const float* K, long long ldk, const float* V,
+                      long long ldv, float* O, long long ldo, const int* key_mask, int causal, int B, int H, int Tq,
+                      int Tk, int head_dim, float scale);
+int mic_f32_embed(void* stream, const int* ids, const float* table, float scale, const float* pos_table, int pos_offset,
+                  int T, float* out, int M, int d);
+int mic_f32_patchify(void* stream, const float* pixels, float* out, int B, int image_size, int patch, int channel_first,
+                     int trunc_int);
+int mic_f32_vit_embed(void* stream, const float* patch_out, const float* patch_bias, const float* cls, const float* pos,
+                      float* out, int B, int S, int d);
+int mic_f32_ce_rows(void* stream, const float* logits, long long ld, const int* labels, int M, int V,
+                    float label_smoothing, float* row_loss, float* lse);
+
 /* profiling aid: n grid barriers of the kind mic_decoder_step uses (tools/microbench_barrier.py) */
 int mic_barrier_bench(void* stream, unsigned int* sync_counter, int n, int variant);
 

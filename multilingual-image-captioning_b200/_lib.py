@@ -25,6 +25,13 @@ SIGNATURES = {
     "mic_decoder_plan_init": [P, P, P, I, P, P, I, I, I, I, I, I, I, L, I, F],
     "mic_decoder_step": [P, P, I, I, I, P, P],
     "mic_barrier_bench": [P, P, I, I],
+    "mic_f32_gemm": [P, P, L, P, L, I, I, I, I, P, I, P, L, P, L],
+    "mic_f32_layernorm": [P, P, P, P, F, P, I, I],
+    "mic_f32_attention": [P, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F],
+    "mic_f32_embed": [P, P, P, F, P, I, I, P, I, I],
+    "mic_f32_patchify": [P, P, P, I, I, I, I, I],
+    "mic_f32_vit_embed": [P, P, P, P, P, P, I, I, I],
+    "mic_f32_ce_rows": [P, P, L, P, I, I, F, P, P],
     "mic_gemm_bf16": [P, I, I, P, L, P, L, I, I, I, P, L, I, I, P, I, P, P, L, I, I, I, P, I, F],
     "mic_lm_head_num_partials": [I],
     "mic_lm_head_ce_stats": [P, P, L, P, L, P, P, I, I, I, P, P, P, P, P, L],

@@ -67,10 +67,16 @@ class FlaxCLIPVisionMBartForConditionalGeneration:
         if not torch.cuda.is_available():
             raise RuntimeError("mic_b200 runs on an NVIDIA B200 (sm_100a) only; no CUDA device is visible")
         lib()  # fail loudly if the extension is missing
-        if str(dtype) not in ("bfloat16", "torch.bfloat16", "bf16"):
-            raise NotImplementedError("compute dtype is bf16 (fp32 master weights); fp32 compute mode is not built yet")
+        if str(dtype) in ("bfloat16", "torch.bfloat16", "bf16"):
+            self.dtype = "bfloat16"
+        elif str(dtype) in ("float32", "torch.float32", "fp32", "f32"):
+            # fp32 VERIFICATION mode (engine_fp32.py): __call__ / loss run with fp32 storage and fp32 SIMT kernels
+            # (BASELINE configs[0]: logits within 1e-3, loss within 1e-4 of the oracle); training and generate()
+            # exist in bf16 only
+            self.dtype = "float32"
+        else:
+            raise NotImplementedError(f"compute dtype {dtype}: bfloat16 (product path) or float32 (verification path)")
         self.config = config
-        self.dtype = "bfloat16"
         self.device = torch.device(device)
         self.store = ParamStore(config, self.device)
         self.engine = CaptionEngine(config, self.store)
@@ -127,6 +133,11 @@ class FlaxCLIPVisionMBartForConditionalGeneration:
         B, T = ids.shape
         mask = torch.ones((B, T), dtype=I32, device=self.device) if decoder_attention_mask is None else \
             _as_tensor(decoder_attention_mask, self.device, I32)
+        if self.dtype == "float32":
+            if decoder_position_ids is not None or train:
+                raise NotImplementedError("fp32 verification mode: default positions, inference only")
+            from .engine_fp32 import Fp32Forward
+            return Seq2SeqLMOutput(logits=Fp32Forward(eng).logits(px, ids, mask), encoder_last_hidden_state=None)
         pos = None if decoder_position_ids is None else _as_tensor(decoder_position_ids, self.device, I32).contiguous().view(-1)
         enc = eng.encode(px, trunc_int=False, save=False, tag="fw.enc")
         enc_kv = eng.cross_kv(enc, tag="fw.enc")
@@ -144,6 +155,9 @@ class FlaxCLIPVisionMBartForConditionalGeneration:
         ids = _as_tensor(decoder_input_ids, self.device, I32)
         B, T = ids.shape
         mask = _as_tensor(attention_mask, self.device, I32).contiguous()
+        if self.dtype == "float32":
+            from .engine_fp32 import Fp32Forward
+            return Fp32Forward(eng).loss(px, ids, mask, _as_tensor(labels, self.device, I32), label_smoothing_factor)[0].float()
         lab = _as_tensor(labels, self.device, I32).contiguous().view(-1)
         enc = eng.encode(px, trunc_int=False, save=False, tag="fw.enc")
         enc_kv = eng.cross_kv(enc, tag="fw.enc")
