@@ -55,5 +55,3 @@ print("  epilogue detail: tmem loaded", f(tr[132:133]), " gelu done", f(tr[133:1
 TA = 1 + 1 + 11 * 5
 t0 = end[TA - 1]
 print(f"fine trace of self_attn/layer5 on CTA 1 warp 4: phase entered {f(tr[169:170])}, items done {f(tr[168:169])}, arrival {(t[TA, 1] - t0) / 1e3:.2f}")
-for it in range(4):
-    print(f"  item {it}: anc loaded / copies issued / q staged / K,V landed / softmax done / output stored:", f(tr[170 + 8 * it: 176 + 8 * it]))
