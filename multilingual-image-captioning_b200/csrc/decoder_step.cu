@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         if (ph.kind > PH_GEMM_RED) continue;
         const int units = m_tiles * ph.n_tiles * ph.split_k;
         if (cta >= units) continue;
+        Unit t = unit_of(ph, cta, m_tiles);              // address arithmetic of the first unit before the wait
         if (p > 0) {
           while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
           fence_acquire_gpu();
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         const bool trc = args.prof && cta == TRACE_CTA && p == TRACE_PHASE;
         if (trc) args.prof[(long long)P * G + 129] = gtime();
         for (int u = cta; u < units; u += G) {
-          const Unit t = unit_of(ph, u, m_tiles);
+          if (u != cta) t = unit_of(ph, u, m_tiles);
           int kb = t.kb_lo + t.rot;
           const int kb_end = t.kb_lo + t.len;
 #pragma unroll 1
