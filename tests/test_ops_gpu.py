@@ -361,6 +361,46 @@ def test_lm_head_search_and_merge():
     np.testing.assert_allclose(got_lp[clear], val[clear], atol=2e-4)
 
 
+@pytest.mark.parametrize("R,V", [(24, 5003), (200, 70001)])
+def test_lm_head_search_packed_equals_unpacked(R, V):
+    """Tile-image operands + bulk copies (mic_lm_head_search_packed, mic_pack_kmajor_tiles) give bit-identical
+    candidates and log-probs to the TMA-box kernel; large vocabulary exercises the two-phase top-8 queue path."""
+    K = 256
+    h, E = rnd(R, K, seed=83), rnd(V, K, seed=84, scale=0.3)
+    bias = rnd(V, seed=85, dtype=torch.float32, scale=0.1)
+    n = ops.lm_head_search_num_partials(R)
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=DEV)
+    def ws_():
+        return {"nparts": n, "pmax": f(n, R), "psum": f(n, R), "cand_val": f(n, R, 8),
+                "cand_idx": torch.empty(n, R, 8, dtype=torch.int32, device=DEV), "row_lp": f(R, 8),
+                "row_tok": torch.empty(R, 8, dtype=torch.int32, device=DEV), "row_ml": f(R, 2)}
+    def aligned(nbytes):
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=DEV)
+        off = (-raw.data_ptr()) % 1024
+        return raw[off:off + nbytes]
+    a, b = ws_(), ws_()
+    ops.lm_head_search(h, E, bias, 7, a)
+    ops.search_merge(a, R)
+    ht, et = aligned(ops.pack_kmajor_tiles_bytes(R, K, 128)), aligned(ops.pack_kmajor_tiles_bytes(V, K, 256))
+    ops.pack_kmajor_tiles(h, 128, ht)
+    ops.pack_kmajor_tiles(E, 256, et)
+    ops.lm_head_search_packed(ht, et, bias, 7, R, V, K, b)
+    ops.search_merge(b, R)
+    torch.cuda.synchronize()
+    assert torch.equal(a["row_tok"], b["row_tok"])
+    assert torch.equal(a["row_lp"], b["row_lp"])
+    # and against torch on the big case: the 8 candidates are the fp32 top-8 wherever the 8th/9th gap is clear
+    z = h.float() @ E.float().t() + bias
+    z[:, 7] = float("-inf")
+    lp = torch.log_softmax(z, -1)
+    val, idx = torch.sort(lp, dim=-1, descending=True, stable=True)
+    clear = (val[:, 7] - val[:, 8]) > 1e-3
+    assert clear.float().mean() > 0.5
+    got = torch.sort(b["row_tok"][clear].long(), dim=-1).values
+    want = torch.sort(idx[clear][:, :8], dim=-1).values
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("split_k", [0, 3, 8])
 def test_gemm_split_k_reduce_add(split_k):
     """wgrad-shaped GEMM (few output tiles, long K) with K slices combined by TMA reduce-add."""
