@@ -201,6 +201,8 @@ typedef struct {
   const float* ln_out_g; const float* ln_out_b;    /* decoder layer_norm                        */
   void* h_out_tiles;                               /* optional: result as a 128-row tile image instead (input of
                                                       mic_lm_head_search_packed); h_out is then not written */
+  const void* cross_kv_tiles;                      /* optional: visual K|V re-packed by mic_decoder_pack_cross_kv
+                                                      ([image][layer][head][16 KB]): one bulk copy per attention item */
 } mic_decoder_buffers_t;
 long long mic_decoder_plan_bytes(int num_layers);
 long long mic_decoder_packed_bytes(int num_layers, int d_model, int ffn_dim);
@@ -208,6 +210,11 @@ long long mic_decoder_packed_bytes(int num_layers, int d_model, int ffn_dim);
  * Capturable; generate() runs it once per call so that updated parameters are always picked up. */
 int mic_decoder_pack_weights(void* stream, const mic_decoder_layer_t* layers, int num_layers, int d_model,
                              int ffn_dim, void* packed);
+/* visual K|V [B*S, ld] (layer l: K at column l*2d, V at l*2d + d) -> per (image, layer, head) a contiguous 16 KB
+ * shared-memory stage image (S <= 64 keys, zero padded).  Capturable; once per generate() call. */
+long long mic_decoder_cross_kv_tiles_bytes(int B, int num_layers, int heads);
+int mic_decoder_pack_cross_kv(void* stream, const void* enc_kv, long long ld, int B, int S, int num_layers, int heads,
+                              int d_model, void* out);
 /* builds the phase table on the host and copies it to plan_dev (128-byte aligned device buffer of
  * mic_decoder_plan_bytes).  Not capturable into a CUDA graph (host staging): call once per buffer set. */
 int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_decoder_layer_t* layers, int num_layers,

@@ -25,6 +25,8 @@ SIGNATURES = {
     "mic_decoder_plan_init": [P, P, P, I, P, P, I, I, I, I, I, I, I, L, I, F],
     "mic_decoder_step": [P, P, I, I, I, P, P],
     "mic_barrier_bench": [P, P, I, I],
+    "mic_decoder_cross_kv_tiles_bytes": [I, I, I],
+    "mic_decoder_pack_cross_kv": [P, P, L, I, I, I, I, I, P],
     "mic_f32_gemm": [P, P, L, P, L, I, I, I, I, P, I, P, L, P, L],
     "mic_f32_layernorm": [P, P, P, P, F, P, I, I],
     "mic_f32_attention": [P, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F],

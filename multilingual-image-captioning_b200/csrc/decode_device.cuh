@@ -191,6 +191,11 @@ struct DecAttnArgs {
   float* q_acc;
   const float* q_bias;
   int o_tiled_kb;        // > 0: o is written in the UMMA tile image layout (tiled_off), = H
+  // persistent-kernel cross-attention: K|V of every (kv row, head) pre-arranged as ONE contiguous 16 KB stage image
+  // (K rows 0..63 then V rows 0..63, 128 B each, chunk c of row j at c ^ (j & 7), rows >= n_keys zero):
+  // element offset = kv_row * kv_tiles_stride + head * 8192.  Null = gather from kc / vc with cp.async.
+  const bf16* kv_tiles;
+  long long kv_tiles_stride;
 };
 
 // s_p: DEC_MAX_KEYS floats, s_row: DEC_MAX_KEYS ints of per-warp shared scratch.  q / k / v go through L2 (ld.global.cg): in the
@@ -694,6 +699,60 @@ __device__ __forceinline__ void decode_self_attn_pipelined(const DecAttnArgs& a,
     cp_async_commit();
     i = inext;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-attention item on pre-packed K|V stage images: the whole 16 KB stage arrives with ONE bulk copy (vs 800
+// 16-byte cp.async), the query rows of the item are loaded while it is in flight.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_cross_attn_packed(const DecAttnArgs& a, int kv_item, int h, uint8_t* kv_smem,
+                                                         bf16* q_stage, uint64_t* bar, uint32_t* parity, int lane) {
+  constexpr int QP = 72;
+  const int nk = a.n_keys;
+  const int rpk = a.rows_per_kv;
+  const int r0 = kv_item * rpk;
+  if (lane == 0) {
+    mbar_arrive_expect_tx(bar, 16384);
+    bulk_load(kv_smem, a.kv_tiles + (long long)kv_item * a.kv_tiles_stride + (long long)h * 8192, 16384, bar);
+  }
+  // queries -> bf16 stage rows 0..rpk-1 (pre-scaled: 1/8 is exact), zero rows rpk..7: 64 16-byte chunks, 2 per lane
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int id = lane + t * 32;
+    const int rr = id >> 3, c8 = (id & 7) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (rr < rpk && r0 + rr < a.R) {
+      const int r = r0 + rr;
+      if (a.q != nullptr) {
+        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
+      } else {
+        float* qa = a.q_acc + (long long)r * a.ldq + h * HD + c8;
+        float b[8];
+        load8f_cg(qa, f);
+        load8f(a.q_bias + h * HD + c8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] + b[j]);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(qa) = z;                  // hand the split-K accumulator back zeroed
+        *reinterpret_cast<float4*>(qa + 4) = z;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= a.scale;
+    }
+    store8(q_stage + rr * QP + c8, f);
+  }
+  __syncwarp();
+  mbar_wait(bar, *parity);
+  *parity ^= 1;
+  const uint32_t kv_base = smem_u32(kv_smem);
+  uint32_t pa[8];
+  float inv;
+  attn_qk_softmax(kv_base, q_stage, nk, lane, pa, &inv);
+  attn_pv_store(a, kv_base, nk, pa, inv, r0, h, lane);
+  __syncwarp();
+  fence_proxy_async();      // generic reads of the stage are ordered before the next item's bulk copy into it
 }
 
 // (A software-pipelined variant that fetched every 128-byte key row with its own cp.async.bulk - cache rows stored

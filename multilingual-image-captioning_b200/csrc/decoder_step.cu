@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
     const int vt = threadIdx.x - 128;          // 0..255 among the vector warps
     const bool leader = threadIdx.x == 128;
     uint32_t it = 0;
+    uint32_t attn_parity = 0;                  // phase parity of this warp's attention-stage barrier
     for (int p = 0; p < P; ++p) {
       const Phase& ph = phases[p];
       if (ph.kind <= PH_GEMM_RED) {
@@ -408,6 +409,10 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           if (tra && lane == 0) args.prof[(long long)P * G + 169] = gtime();
           if (ph.keys_from_pos && a.q != nullptr) {
             decode_self_attn_pipelined(a, gw, nw, items, kv_stage, reinterpret_cast<bf16*>(q_smem), lane);
+          } else if (a.kv_tiles != nullptr) {
+            for (int i = gw; i < items; i += nw)
+              decode_cross_attn_packed(a, i / a.H, i % a.H, kv_stage, reinterpret_cast<bf16*>(q_smem), &attn_bar[ew],
+                                       &attn_parity, lane);
           } else {
             for (int i = gw; i < items; i += nw) {
               int row0, row1;
@@ -501,7 +506,39 @@ __global__ void __launch_bounds__(128) pack_weight_tiles_kernel(const PackJobs j
   }
 }
 
+// ---- cross K|V re-pack: enc_kv [B*S, ld] (layer l: K at l*2d, V at l*2d + d) -> [image][layer][head] stage images
+// ---- of 16 KB (K rows 0..63, V rows 0..63; 128 B rows, chunk c of row j at c ^ (j & 7); rows >= S zero)
+__global__ void __launch_bounds__(256) pack_cross_kv_kernel(const bf16* __restrict__ enc_kv, long long ld, int B,
+                                                            int S, int L, int H, int d, bf16* __restrict__ out) {
+  const long long items = (long long)B * L * H;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int h = (int)(it % H), l = (int)((it / H) % L), b = (int)(it / ((long long)H * L));
+    bf16* dst = out + it * 8192;
+    for (int i = threadIdx.x; i < 2 * 64 * 8; i += 256) {
+      const int c = i & 7, j = (i >> 3) & 63, kv = i >> 9;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (j < S) v = *reinterpret_cast<const uint4*>(enc_kv + ((long long)b * S + j) * ld + (long long)l * 2 * d + kv * d + h * 64 + c * 8);
+      *reinterpret_cast<uint4*>(dst + kv * 4096 + j * 64 + ((c ^ (j & 7)) << 3)) = v;
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" long long mic_decoder_cross_kv_tiles_bytes(int B, int num_layers, int heads) {
+  return (long long)B * num_layers * heads * 16384;
+}
+extern "C" int mic_decoder_pack_cross_kv(void* stream, const void* enc_kv, long long ld, int B, int S, int num_layers,
+                                         int heads, int d_model, void* out) {
+  MIC_CHECK_ARG(enc_kv && out && S >= 1 && S <= 64 && d_model == heads * 64, "pack_cross_kv: S=%d must be <= 64", S);
+  MIC_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 1023) == 0, "pack_cross_kv: output must be 1024-byte aligned");
+  const long long items = (long long)B * num_layers * heads;
+  const int grid = (int)(items < 148ll * 8 ? items : 148ll * 8);
+  pack_cross_kv_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)enc_kv, ld, B, S, num_layers,
+                                                                                 heads, d_model, (bf16*)out);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // host side: the plan (phase table) lives in a caller-provided device buffer
@@ -618,7 +655,7 @@ extern "C" int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_dec
     sa.q = (const bf16*)buf->q; sa.ldq = d; sa.kc = (const bf16*)w.self_kv; sa.vc = (const bf16*)w.self_kv + d;
     sa.ldkv = 2 * d; sa.anc = buf->ancestors; sa.T = cache_len; sa.n_keys = 1; sa.rows_per_kv = 1;
     sa.o = (bf16*)buf->o_tiles; sa.ldo = d; sa.R = R; sa.H = heads; sa.scale = scale; sa.q_acc = nullptr;
-    sa.q_bias = nullptr; sa.o_tiled_kb = d / BK;
+    sa.q_bias = nullptr; sa.o_tiled_kb = d / BK; sa.kv_tiles = nullptr; sa.kv_tiles_stride = 0;
     // 2-3: out_proj (split-K into acc), residual + encoder_attn_layer_norm
     gemm(p[2], PH_GEMM_RED, o_t, pk + 3ll * d * d, d, d, 4, nullptr, buf->acc, d);
     ln(p[3], buf->acc, w.sa_o_b, w.ln_ca_g, w.ln_ca_b, buf->a_tiles, d / BK);
@@ -631,6 +668,10 @@ extern "C" int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_dec
     ca.anc = nullptr; ca.T = enc_tokens; ca.n_keys = enc_tokens; ca.rows_per_kv = rows_per_image;
     ca.o = (bf16*)buf->o_tiles; ca.ldo = d; ca.R = R; ca.H = heads; ca.scale = scale; ca.q_acc = buf->q_acc;
     ca.q_bias = w.ca_q_b; ca.o_tiled_kb = d / BK;
+    if (buf->cross_kv_tiles) {           // [image][layer][head][16 KB]
+      ca.kv_tiles = (const bf16*)buf->cross_kv_tiles + (long long)l * heads * 8192;
+      ca.kv_tiles_stride = (long long)L * heads * 8192;
+    }
     // 6-7: cross out_proj, residual + final_layer_norm
     gemm(p[6], PH_GEMM_RED, o_t, pk + 5ll * d * d, d, d, 4, nullptr, buf->acc, d);
     ln(p[7], buf->acc, w.ca_o_b, w.ln_f_g, w.ln_f_b, buf->a_tiles, d / BK);

@@ -108,7 +108,9 @@ def _fused_plan(engine, cache: DecodeCache, tiled_out=False):
             "a_tiles": _aligned(engine, "gen.a_tiles", Rp * d * 2), "o_tiles": _aligned(engine, "gen.o_tiles", Rp * d * 2),
             "g_tiles": _aligned(engine, "gen.g_tiles", Rp * F * 2), "ancestors": cache.ancestors,
             "ln_out_g": ps.f("d.ln_final.scale"), "ln_out_b": ps.f("d.ln_final.bias"),
-            "h_out_tiles": _aligned(engine, "gen.h_tiles", Rp * d * 2) if tiled_out else None}
+            "h_out_tiles": _aligned(engine, "gen.h_tiles", Rp * d * 2) if tiled_out else None,
+            "cross_kv_tiles": _aligned(engine, "gen.xkv_tiles", ops.decoder_cross_kv_tiles_bytes(
+                R // cache.rows_per_image, L, t.decoder_attention_heads))}
     for n in ("acc", "q_acc"):
         bufs[n] = b.zeros("gen." + n, (R, d))                        # zeroed once; the kernel hands it back zeroed
     packed = _aligned(engine, "gen.wpack", ops.decoder_packed_bytes(L, d, F))
@@ -157,6 +159,8 @@ def fused_prepare(engine, cache: DecodeCache, packed_search=False):
     t = engine.t
     fp = _fused_plan(engine, cache, tiled_out=packed_search)
     ops.decoder_pack_weights(fp["layers"], t.d_model, t.decoder_ffn_dim, fp["packed"])
+    ops.decoder_pack_cross_kv(cache.enc_kv, cache.rows // cache.rows_per_image, engine.c.num_tokens, t.decoder_layers,
+                              t.decoder_attention_heads, t.d_model, fp["bufs"]["cross_kv_tiles"])
     if packed_search:
         emb = engine.ps.w("shared")
         fp["e_tiles"] = _aligned(engine, "gen.e_tiles", ops.pack_kmajor_tiles_bytes(emb.shape[0], emb.shape[1], 256))

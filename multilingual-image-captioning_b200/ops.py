@@ -178,7 +178,7 @@ def residual_ln_fwd(acc, bias, x, gamma, beta, eps, out):
 _LAYER_FIELDS = ("ln_sa_g", "ln_sa_b", "sa_qkv_w", "sa_qkv_b", "sa_o_w", "sa_o_b", "ln_ca_g", "ln_ca_b", "ca_q_w", "ca_q_b",
                  "ca_o_w", "ca_o_b", "ln_f_g", "ln_f_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "self_kv", "enc_k", "enc_v")
 _BUFFER_FIELDS = ("x", "q", "a_tiles", "o_tiles", "g_tiles", "acc", "q_acc", "ancestors", "h_out", "ln_out_g", "ln_out_b",
-                  "h_out_tiles")
+                  "h_out_tiles", "cross_kv_tiles")
 
 
 class DecoderLayerT(ctypes.Structure):        # mic_decoder_layer_t
@@ -219,6 +219,14 @@ def decoder_plan_init(plan, layers_struct, buffers, packed, R, d_model, heads, f
     _call("mic_decoder_plan_init", _p(plan), ctypes.cast(layers_struct, ctypes.c_void_p), len(layers_struct),
           ctypes.cast(ctypes.pointer(bt), ctypes.c_void_p), _p(packed), R, d_model, heads, ffn_dim, cache_len,
           enc_tokens, rows_per_image, ld_enc, ACT[act], eps)
+
+
+def decoder_cross_kv_tiles_bytes(B, num_layers, heads):
+    return lib().mic_decoder_cross_kv_tiles_bytes(B, num_layers, heads)
+
+
+def decoder_pack_cross_kv(enc_kv, B, S, num_layers, heads, d_model, out):
+    _call("mic_decoder_pack_cross_kv", _p(enc_kv), _ld(enc_kv), B, S, num_layers, heads, d_model, _p(out))
 
 
 def decoder_step(plan, num_layers, R, pos, sync, phase_times=None):
