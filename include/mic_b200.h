@@ -45,6 +45,9 @@ int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static);
  * main.py:696 [L2].  D is bf16 (d_is_f32=0) or fp32; accumulate=1 adds into an fp32 D.
  * D2 (optional, bf16, ld = ldd) receives the pre-activation.  block_n/group_m/split_k = 0 -> auto
  * (split_k > 1 cuts K into slices combined by TMA reduce-add; fp32 outputs only).
+ * act < 0 (= -MIC_ACT_*): D = (A * B^T) o act'(U) with U (bf16 [M, ldr], the saved pre-activation of the layer
+ * below) passed as `residual`: the dgrad contraction of fc2 fused with the activation backward of fc1
+ * (K-major operands, bf16 output, no bias / D2 / dropout).
  * drop_seed (device u32, null = off): flax.linen.Dropout(rate=drop_p) on the activation output BEFORE the
  * residual add — FlaxMBartDecoderLayer `hidden_states = residual + dropout(...)`; the mask is a counter
  * hash of (*drop_seed + drop_site, element index), regenerated identically by mic_act_bwd_colsum. */

@@ -243,6 +243,15 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
       ep.accumulate = 1;
     }
   }
+  if (act < 0) {
+    // D = (A B^T) o act'(U): dgrad GEMM fused with the activation backward of the layer below; U enters as `residual`
+    MIC_CHECK_ARG(!a_mn_major && !b_mn_major && tma && residual && !bias && !D2 && !d_is_f32 && o.bn == 256 &&
+                      !ep.drop.seed_ptr,
+                  "fused activation backward needs the (K,K) layout, bf16 TMA output, the pre-activation as `residual` "
+                  "and 256-wide tiles");
+    ep.act = -act;
+    return launch_one<0, 0, 256, EpiStoreActBwd16>(s, o, ep);
+  }
   if (!a_mn_major && b_mn_major && act != MIC_ACT_NONE && tma && o.bn == 256)
     return launch_one<0, 1, 256, EpiStoreAct16>(s, o, ep);
   if (!a_mn_major && b_mn_major) return launch_bn<0, 1, EpiStore>(s, o, ep);

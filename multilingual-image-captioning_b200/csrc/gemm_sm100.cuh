@@ -128,7 +128,10 @@ struct EpiStoreParams {
 
 // NBUF = 2: a second staging buffer per warp carries the pre-activation copy (D2), so the two outputs of a
 // group alternate buffers and never wait on each other's TMA read (used for the fc1 GEMMs of training).
-template <int NBUF_, int EW_ = NUM_EPI_WARPS>
+// ACT_BWD = true (EpiStoreActBwd16): the `residual` tile is the saved pre-activation U of the PREVIOUS layer and
+// the result is multiplied by act'(U) instead of added to it - the fc2 dgrad GEMM then emits d(fc1 pre-activation)
+// directly and the separate activation-backward pass over [M, ffn] (read dG, read U, write dU) disappears.
+template <int NBUF_, int EW_ = NUM_EPI_WARPS, bool ACT_BWD = false>
 struct EpiStoreT {
   static constexpr int NBUF = NBUF_;
   static constexpr int EW = EW_;
@@ -237,7 +240,19 @@ struct EpiStoreT {
         }
       }
     }
-    if (p.act != MIC_ACT_NONE) {
+    if constexpr (ACT_BWD) {
+      if (p.residual) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float* x = v + u * 8;
+          float2 f;
+          f = unpack_bf16(res[u].x); x[0] *= act_bwd(f.x, p.act); x[1] *= act_bwd(f.y, p.act);
+          f = unpack_bf16(res[u].y); x[2] *= act_bwd(f.x, p.act); x[3] *= act_bwd(f.y, p.act);
+          f = unpack_bf16(res[u].z); x[4] *= act_bwd(f.x, p.act); x[5] *= act_bwd(f.y, p.act);
+          f = unpack_bf16(res[u].w); x[6] *= act_bwd(f.x, p.act); x[7] *= act_bwd(f.y, p.act);
+        }
+      }
+    } else if (p.act != MIC_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = act_fwd(v[j], p.act);
     }
@@ -252,7 +267,7 @@ struct EpiStoreT {
         v[2 * j + 1] = k1 ? v[2 * j + 1] * p.drop.scale : 0.f;
       }
     }
-    if (p.residual) {
+    if (!ACT_BWD && p.residual) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         float* x = v + u * 8;
@@ -294,6 +309,7 @@ struct EpiStoreT {
 typedef EpiStoreT<1> EpiStore;
 typedef EpiStoreT<2> EpiStoreDual;
 typedef EpiStoreT<1, 16> EpiStoreAct16;      // 16 epilogue warps: GELU / quick-GELU epilogues are issue bound
+typedef EpiStoreT<1, 16, true> EpiStoreActBwd16;   // dgrad GEMM fused with the activation backward of its consumer
 
 // --------------------------------------------------------------------------------------------
 // Epilogue policy 1: lm_head + log-softmax / label-smoothed CE statistics (no logits written)

@@ -68,6 +68,11 @@ class CaptionEngine:
         self.Vp = (self.t.vocab_size + 255) // 256 * 256
         self.emb_scale = math.sqrt(self.t.d_model) if self.t.scale_embedding else 1.0
         self._ws = None
+        import os
+        # fc2 dgrad GEMM applying act'(u) of fc1 in its epilogue (mic_gemm_bf16 act < 0): parity-tested, but measured
+        # 1 % SLOWER than the separate activation-backward pass (74.3 vs 73.4 ms/step: the 16-warp epilogue is
+        # register-starved) -> off by default
+        self.fuse_act_bwd = os.environ.get("MIC_FUSE_ACT_BWD", "0") != "0"
         # decoder dropout (flax.linen.Dropout, rate = mbart_config.dropout) — active only inside train steps
         self.dropout_p = 0.0
         self.drop_seed = torch.zeros(1, dtype=I32, device=self.dev)
@@ -136,7 +141,7 @@ class CaptionEngine:
         return dx
 
     def _dense_bwd(self, x, dy, wname, dx_out, bias=True, w_view=None, gw_view=None, gb_view=None, act=None, u=None,
-                   du=None, dropout=None, dgrad_residual=None):
+                   du=None, dropout=None, dgrad_residual=None, dgrad_act_bwd=None):
         """Backward of y = act(x @ W + b).  x: [M,K] input, dy: [M,N] grad of the output (post-act).
         Returns dx (written into dx_out) — or None if dx_out is None."""
         ps = self.ps
@@ -163,7 +168,9 @@ class CaptionEngine:
         self._fork_side(lambda: ops.gemm(x, dyv, a_mn=True, b_mn=True, out=gw), x, dyv, gw)   # dW[K,N] = x^T dy
         if dx_out is not None:
             self._before_write(dx_out)
-            ops.gemm(dy, w, a_mn=False, b_mn=False, out=dx_out, residual=dgrad_residual)   # dx[M,K] = dy W^T (+ skip grad)
+            # dx[M,K] = dy W^T (+ skip grad), or fused with the activation backward of the layer that produced x:
+            # dgrad_act_bwd = (act, U): dx = (dy W^T) o act'(U)
+            ops.gemm(dy, w, a_mn=False, b_mn=False, out=dx_out, residual=dgrad_residual, act_bwd=dgrad_act_bwd)
         return dx_out
 
     # ------------------------------------------------------------------------------------------
@@ -332,8 +339,13 @@ class CaptionEngine:
             g_, u_, lnF = b.t[tg + ".g" + sfx], b.t[tg + ".u" + sfx], b.t[tg + ".lnF" + sfx]
             x2, x1, x0 = b.t[tg + ".x2" + sfx], b.t[tg + ".x1" + sfx], b.t[tg + f".x{l}"]
             # FFN
-            self._dense_bwd(g_, dx, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
-            self._dense_bwd(lnF, dg, n + ".fc1", dtmp, act=t.activation_function, u=u_, du=du)
+            if self.fuse_act_bwd:      # fc2 dgrad emits d(fc1 pre-activation) directly: dg = (dx W2^T) o act'(u)
+                self._dense_bwd(g_, dx, n + ".fc2", dg, dropout=self._drop(12 + 4 * l),
+                                dgrad_act_bwd=(t.activation_function, u_))
+                self._dense_bwd(lnF, dg, n + ".fc1", dtmp)
+            else:
+                self._dense_bwd(g_, dx, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
+                self._dense_bwd(lnF, dg, n + ".fc1", dtmp, act=t.activation_function, u=u_, du=du)
             self._ln_bwd(dtmp, x2, n + ".ln_f", (b.t[tg + ".lnF.mean" + sfx], b.t[tg + ".lnF.rstd" + sfx]), dx, dx)
             # cross attention
             ca, qc, lnC = b.t[tg + ".ca" + sfx], b.t[tg + ".qc" + sfx], b.t[tg + ".lnC" + sfx]
@@ -373,9 +385,14 @@ class CaptionEngine:
                 return (b.t[tg + nm + ".mean" + sfx], b.t[tg + nm + ".rstd" + sfx])
             # FFN block: x3 = LN(y3), y3 = x2 + drop(fc2(gelu(fc1(x2))))
             self._ln_bwd(dx, b.t[tg + ".y3" + sfx], n + ".ln_f", st(".lnF"), None, dy)
-            self._dense_bwd(b.t[tg + ".g" + sfx], dy, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
-            self._dense_bwd(b.t[tg + ".x2" + sfx], dg, n + ".fc1", dx, act=t.activation_function, u=b.t[tg + ".u" + sfx],
-                            du=du, dgrad_residual=dy)                                  # dx2 = dy3 + fc1 dgrad
+            if self.fuse_act_bwd:
+                self._dense_bwd(b.t[tg + ".g" + sfx], dy, n + ".fc2", dg, dropout=self._drop(12 + 4 * l),
+                                dgrad_act_bwd=(t.activation_function, b.t[tg + ".u" + sfx]))
+                self._dense_bwd(b.t[tg + ".x2" + sfx], dg, n + ".fc1", dx, dgrad_residual=dy)   # dx2 = dy3 + fc1 dgrad
+            else:
+                self._dense_bwd(b.t[tg + ".g" + sfx], dy, n + ".fc2", dg, dropout=self._drop(12 + 4 * l))
+                self._dense_bwd(b.t[tg + ".x2" + sfx], dg, n + ".fc1", dx, act=t.activation_function,
+                                u=b.t[tg + ".u" + sfx], du=du, dgrad_residual=dy)      # dx2 = dy3 + fc1 dgrad
             # cross-attention block
             self._ln_bwd(dx, b.t[tg + ".y2" + sfx], n + ".ln_ca", st(".lnC"), None, dy)
             self._dense_bwd(b.t[tg + ".ca" + sfx], dy, n + ".ca_o", dtmp, dropout=self._drop(11 + 4 * l))
@@ -532,8 +549,12 @@ class CaptionEngine:
             sfx = f".{l}"
             g_, u_, ln2 = b.t[te + ".g" + sfx], b.t[te + ".u" + sfx], b.t[te + ".ln2" + sfx]
             xm, x0 = b.t[te + ".xm" + sfx], b.t[te + f".x{l}"]
-            self._dense_bwd(g_, dxv, n + ".fc2", dgv)
-            self._dense_bwd(ln2, dgv, n + ".fc1", dvt, act=c.hidden_act, u=u_, du=duv)
+            if self.fuse_act_bwd:
+                self._dense_bwd(g_, dxv, n + ".fc2", dgv, dgrad_act_bwd=(c.hidden_act, u_))
+                self._dense_bwd(ln2, dgv, n + ".fc1", dvt)
+            else:
+                self._dense_bwd(g_, dxv, n + ".fc2", dgv)
+                self._dense_bwd(ln2, dgv, n + ".fc1", dvt, act=c.hidden_act, u=u_, du=duv)
             self._ln_bwd(dvt, xm, n + ".ln2", (b.t[te + ".ln2.mean" + sfx], b.t[te + ".ln2.rstd" + sfx]), dxv, dxv)
             att, qkv, ln1 = b.t[te + ".att" + sfx], b.t[te + ".qkv" + sfx], b.t[te + ".ln1" + sfx]
             self._dense_bwd(att, dxv, n + ".o", dvt)

@@ -60,7 +60,7 @@ def _ld(t):
 # GEMM family
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, act="none", pre_act_out=None,
-         residual=None, accumulate=False, block_n=0, group_m=0, split_k=0, dropout=None):
+         residual=None, accumulate=False, block_n=0, group_m=0, split_k=0, dropout=None, act_bwd=None):
     """D[M,N] = act(A[M,K] B[N,K]^T + bias) + residual.
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True, Flax kernel)."""
     assert a.dtype == BF16 and b.dtype == BF16
@@ -81,8 +81,12 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, a
         assert pre_act_out.dtype == BF16 and _ld(pre_act_out) == _ld(out)
     if bias is not None:
         assert bias.dtype == F32 and bias.numel() == N
+    act_code = ACT[act]
+    if act_bwd is not None:          # (activation name, saved pre-activation U): D = (A B^T) o act'(U)
+        assert residual is None and bias is None and act_code == 0
+        act_code, residual, block_n = -ACT[act_bwd[0]], act_bwd[1], 256
     _call("mic_gemm_bf16", int(a_mn), int(b_mn), _p(a), _ld(a), _p(b), _ld(b), M, N, K, _p(out), _ld(out),
-          int(d_f32), int(accumulate), _p(bias), ACT[act], _p(pre_act_out), _p(residual),
+          int(d_f32), int(accumulate), _p(bias), act_code, _p(pre_act_out), _p(residual),
           _ld(residual) if residual is not None else 0, block_n, group_m, split_k, *_drop(dropout))
     return out
 
