@@ -309,7 +309,7 @@ struct EpiStoreT {
 typedef EpiStoreT<1> EpiStore;
 typedef EpiStoreT<2> EpiStoreDual;
 typedef EpiStoreT<1, 16> EpiStoreAct16;      // 16 epilogue warps: GELU / quick-GELU epilogues are issue bound
-typedef EpiStoreT<1, 16, true> EpiStoreActBwd16;   // dgrad GEMM fused with the activation backward of its consumer
+typedef EpiStoreT<1, 8, true> EpiStoreActBwd16;    // dgrad GEMM fused with the activation backward of its consumer (8 warps: the 16-warp form is register-starved)
 
 // --------------------------------------------------------------------------------------------
 // Epilogue policy 1: lm_head + log-softmax / label-smoothed CE statistics (no logits written)
