@@ -9,7 +9,7 @@ from mic_b200 import synthetic, generation as gen, ops
 cfg = mic_b200.clip_mbart_config()
 model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, seed=0)
 eng = model.engine
-B, K, T = 64, 4, 64
+B, K, T = (int(sys.argv[2]) if len(sys.argv) > 2 else 64), 4, 64
 R = B * K
 px = torch.from_numpy(synthetic.make_batch(cfg, B, 64, seed=7)["pixel_values"]).cuda()
 enc = eng.encode(px, trunc_int=True, save=False, tag="gen.enc")
