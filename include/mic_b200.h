@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MIC_B200_ABI_VERSION 1
+#define MIC_B200_ABI_VERSION 2
 
 #define MIC_ACT_NONE 0
 #define MIC_ACT_GELU 1       /* exact erf gelu: FlaxMBartDecoderLayer / ViT MLP */
@@ -86,10 +86,13 @@ int mic_lm_head_ce_grad(void* stream, const void* H, long long ldh, const void* 
 int mic_lm_head_search_num_partials(int M);
 /* upper_val / upper_idx (optional, [M]): second pass for 5..8 beams - only (logit, token) pairs ranking strictly
  * after the row's pair are considered (pass the 8th best of the first pass, mic_search_merge last_val/last_idx);
- * the partial statistics of such a pass are meaningless. */
+ * the partial statistics of such a pass are meaningless.
+ * active (optional): device flag of the search loop's while_loop condition (generation_clip_vision_utils.py:798-820);
+ * 0 = the loop has ended, the kernel returns without touching its outputs. */
 int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
                        const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
-                       float* cand_val, int* cand_idx, const float* upper_val, const int* upper_idx);
+                       float* cand_val, int* cand_idx, const float* upper_val, const int* upper_idx,
+                       const int* active);
 
 /* packed-operand variant of mic_lm_head_search: H and E are given as K-major tile images (mic_pack_kmajor_tiles:
  * H with tile_rows = 128 - the persistent decoder step writes it directly -, E with tile_rows = 256), so that a
@@ -99,7 +102,7 @@ long long mic_pack_kmajor_tiles_bytes(long long rows, int K, int tile_rows);
 int mic_pack_kmajor_tiles(void* stream, const void* src, long long ld, long long rows, int K, int tile_rows, void* out);
 int mic_lm_head_search_packed(void* stream, const void* h_tiles, const void* e_tiles, const float* bias,
                               int mask_token, int M, int V, int K, float* pmax, float* psum, float* cand_val,
-                              int* cand_idx, const float* upper_val, const int* upper_idx);
+                              int* cand_idx, const float* upper_val, const int* upper_idx, const int* active);
 
 /* ---- normalisation / embedding / elementwise (HBM-bound, vectorised, warp-shuffle reductions) ----
  * flax.linen.LayerNorm (fp32 statistics, var = E[x^2]-E[x]^2) as used by FlaxCLIPEncoderLayer,
@@ -144,9 +147,12 @@ int mic_vit_embed_ln_fwd(void* stream, const void* patch_out, const float* patch
                          void* y, float* mean, float* rstd, int B, int S, int d);
 int mic_drop_cls_rows(void* stream, const void* d_emb, void* out, int B, int S, int d);
 /* optax.adamw main.py:629-635 + TrainState.apply_gradients :701 [O1]; flat fp32 p/m/v/g, bf16 shadow.
- * hyper_dev (device, 8 floats): lr, b1, b2, eps, weight_decay, 1/(1-b1^t), 1/(1-b2^t), grad_scale */
-int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* shadow_bf16, const float* hyper_dev,
-              long long n);
+ * The step's scalars travel BY VALUE as kernel arguments (bias_corr1 = 1/(1-b1^t), bias_corr2 = 1/(1-b2^t),
+ * grad_scale = 1/world for the pmean of main.py:698): a host that runs ahead of the stream can never change
+ * them under an already enqueued update. */
+int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* shadow_bf16, long long n, float lr,
+              float b1, float b2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
+              float grad_scale);
 int mic_cast_f32_to_bf16(void* stream, const float* in, void* out, long long n);
 
 /* ---- attention ------------------------------------------------------------------------------------
@@ -191,7 +197,9 @@ typedef struct {
   const float* ln_f_g;  const float* ln_f_b;       /* final_layer_norm (before the FFN)         */
   const void* fc1_w;    const float* fc1_b;        /* [d, ffn], [ffn]                           */
   const void* fc2_w;    const float* fc2_b;        /* [ffn, d], [d]                             */
-  void* self_kv;                                   /* [R, cache_len, 2d] bf16: k | v            */
+  void* self_kv;                                   /* bf16, R * cache_len * 2d elements, HEAD-MAJOR:
+                                                      [row][head][K plane | V plane][pos][64], 16-byte chunk c of a
+                                                      (pos) row stored at c ^ (pos & 7); private to the fused step */
   const void* enc_k;    const void* enc_v;         /* visual K / V of this layer, row pitch ld_enc */
 } mic_decoder_layer_t;
 typedef struct {
@@ -224,11 +232,16 @@ int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_decoder_layer_
                           const mic_decoder_buffers_t* buffers, const void* packed, int R, int d_model, int heads,
                           int ffn_dim, int cache_len, int enc_tokens, int rows_per_image, long long ld_enc, int act,
                           float eps);
-/* sync_counter: one uint32, zero before the first call (the kernel leaves it zero).  Capturable.
+/* sync_counter: 256 uint32 (1 KB), zero before the first call (barrier state; the kernel keeps it consistent).
+ * Capturable.
  * phase_times (optional, NULL = off): [1 + 11 * num_layers, #SMs] (+256 trace slots) %globaltimer stamp of each
- * CTA's arrival at the end of each phase (profiling aid: tools/profile_decoder_step.py). */
+ * CTA's arrival at the end of each phase (profiling aid: tools/profile_decoder_step.py).
+ * active (optional): device flag of the search loop's while_loop condition (generation_clip_vision_utils.py:798-820,
+ * written by mic_beam_cond / mic_greedy_cond); 0 = the loop has ended and the step is skipped.
+ * opts: bit 0 = no writer-side generic->async proxy fences, bit 1 = per-CTA flag barrier instead of the counter
+ * (tuning switches; results identical). */
 int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, int pos, unsigned int* sync_counter,
-                     unsigned long long* phase_times);
+                     unsigned long long* phase_times, const int* active, int opts);
 
 /* ---- fp32 verification path (fp32 storage, fp32 SIMT arithmetic; forward + loss only) ------------------------
  * For the parity bar of BASELINE configs[0] (B = 8, fp32: logits within 1e-3 relative, loss within 1e-4 of the

@@ -23,7 +23,7 @@ SIGNATURES = {
     "mic_decoder_packed_bytes": [I, I, I],
     "mic_decoder_pack_weights": [P, P, I, I, I, P],
     "mic_decoder_plan_init": [P, P, P, I, P, P, I, I, I, I, I, I, I, L, I, F],
-    "mic_decoder_step": [P, P, I, I, I, P, P],
+    "mic_decoder_step": [P, P, I, I, I, P, P, P, I],
     "mic_barrier_bench": [P, P, I, I],
     "mic_decoder_cross_kv_tiles_bytes": [I, I, I],
     "mic_decoder_pack_cross_kv": [P, P, L, I, I, I, I, I, P],
@@ -42,10 +42,10 @@ SIGNATURES = {
     "mic_ce_finalize": [P, P, P, P, P, P, I, I, I, F, P, P, P, P],
     "mic_lm_head_ce_grad": [P, P, L, P, L, P, P, P, P, F, F, I, I, I, P, L],
     "mic_lm_head_search_num_partials": [I],
-    "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P, P, P],
+    "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P, P, P, P],
     "mic_pack_kmajor_tiles_bytes": [L, I, I],
     "mic_pack_kmajor_tiles": [P, P, L, L, I, I, P],
-    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
+    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "mic_layernorm_fwd": [P, P, P, P, F, P, P, P, I, I],
     "mic_residual_ln_fwd": [P, P, P, P, P, P, F, P, I, I],
     "mic_layernorm_bwd_workspace_floats": [I, I],
@@ -58,7 +58,7 @@ SIGNATURES = {
     "mic_patchify": [P, P, P, I, I, I, I, I],
     "mic_vit_embed_ln_fwd": [P, P, P, P, P, P, P, F, I, P, P, P, P, I, I, I],
     "mic_drop_cls_rows": [P, P, P, I, I, I],
-    "mic_adamw": [P, P, P, P, P, P, P, L],
+    "mic_adamw": [P, P, P, P, P, P, L, F, F, F, F, F, F, F, F],
     "mic_cast_f32_to_bf16": [P, P, P, L],
     "mic_attention_fwd": [P, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, F],
     "mic_attention_bwd": [P, P, L, P, L, P, L, P, L, P, L, P, P, I, P, L, P, L, P, L, I, I, I, I, I, F],
@@ -106,7 +106,7 @@ def lib() -> C.CDLL:
         fn.restype = L if name.endswith(("_workspace_floats", "_plan_bytes", "_packed_bytes", "_tiles_bytes")) else I
     l.mic_last_error.argtypes = []
     l.mic_last_error.restype = C.c_char_p
-    if l.mic_abi_version() != 1:
+    if l.mic_abi_version() != 2:
         raise MicError("libmic_b200.so ABI version mismatch")
     _lib = l
     return l

@@ -125,7 +125,7 @@ def vit_bart_config() -> CLIPVisionMBartConfig:
     v = CLIPVisionConfig(patch_size=16, hidden_act="gelu", layer_norm_eps=1e-12, patch_bias=True,
                          pre_layernorm=False, final_layernorm=True, channel_first_input=True)
     t = MBartConfig(vocab_size=50265, scale_embedding=False, pre_layernorm=False, final_layer_norm=False,
-                    layer_norm_eps=1e-5, forced_eos_token_id=2, num_beams=4, max_length=20,
+                    layer_norm_eps=1e-6, forced_eos_token_id=2, num_beams=4, max_length=20,
                     decoder_start_token_id=2)
     return CLIPVisionMBartConfig(v, t, model_type="vit-bart")
 
@@ -147,5 +147,5 @@ def tiny_vit_bart_config(vocab_size: int = 1003, layers: int = 2, image_size: in
                          pre_layernorm=False, final_layernorm=True, channel_first_input=True)
     t = MBartConfig(vocab_size=vocab_size, d_model=128, decoder_layers=layers, decoder_attention_heads=2,
                     decoder_ffn_dim=256, max_position_embeddings=128, scale_embedding=False, pre_layernorm=False,
-                    final_layer_norm=False, layer_norm_eps=1e-5)
+                    final_layer_norm=False, layer_norm_eps=1e-6)
     return CLIPVisionMBartConfig(v, t, model_type="vit-bart")

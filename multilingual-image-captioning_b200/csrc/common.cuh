@@ -258,6 +258,25 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Flag-array grid barrier (one word per CTA, holding the number of phases that CTA has completed; a launch-epoch base
+// makes the values monotonic across launches, so nothing is ever reset).  Arrival = one st.release to the CTA's own
+// word: unlike N atomics on ONE word, the arrivals do not serialise in the L2 atomic unit.  A whole warp polls: each
+// lane reads ceil(G/32) words.  Wrap-safe signed comparison.
+__device__ __forceinline__ void flags_wait_warp(const unsigned int* flags, int G, unsigned int target, int lane) {
+  for (;;) {
+    bool ok = true;
+    for (int i = lane; i < G; i += 32) {
+      unsigned int v;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+      ok = ok && (int)(v - target) >= 0;
+    }
+    if (__all_sync(0xffffffffu, ok)) break;
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 __device__ __forceinline__ unsigned int atom_add_release_gpu(unsigned int* p, unsigned int v) {
   unsigned int old;
   asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");

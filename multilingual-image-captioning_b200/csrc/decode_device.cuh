@@ -702,6 +702,111 @@ __device__ __forceinline__ void decode_self_attn_pipelined(const DecAttnArgs& a,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Self-attention items of one warp on the HEAD-MAJOR cache of the persistent kernel (round 2).
+//
+// Cache layout per layer: [row][head][K plane | V plane][pos][64] bf16 (row pitch T*2*H*64 elements, as before), the
+// eight 16-byte chunks of a 128-byte (pos) row stored at chunk c ^ (pos & 7) — i.e. exactly the stage image the MMA
+// path reads.  The K (or V) history of ONE cache row and head is therefore contiguous over positions, and a beam's
+// history is a handful of RUNS of positions that live in the same cache row (its ancestry changes rows only where the
+// beam search re-parented it).  An item's operand is fetched with one bulk copy per run (typically 1-4) instead of
+// 2 * n_keys * 8 = ~650 sixteen-byte cp.async whose issue alone cost 1.3 us per item (profiles/r01_decoder_step_phases
+// .txt: 18 us per self-attention phase).  Worst case (ancestry alternating every position) degrades to one 128-byte
+// copy per key: correct, only slower.
+//   kc = layer base of the cache, T = cache length; rows of keys (lane, lane+32) come from decode_attn_rows().
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void attn_issue_runs(const bf16* plane, long long rowpitch, int nk, int row0, int row1,
+                                                uint8_t* dst, uint64_t* bar, int lane) {
+  const int prev0 = __shfl_up_sync(0xffffffffu, row0, 1);
+  int prev1 = __shfl_up_sync(0xffffffffu, row1, 1);
+  const int last0 = __shfl_sync(0xffffffffu, row0, 31);
+  if (lane == 0) prev1 = last0;
+  const bool s0 = lane < nk && (lane == 0 || row0 != prev0);
+  const bool s1 = lane + 32 < nk && row1 != prev1;
+  const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, s0) |
+                               ((unsigned long long)__ballot_sync(0xffffffffu, s1) << 32);
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)nk * 128u);
+  __syncwarp();
+  if (s0) {
+    const int k = lane;
+    const unsigned long long rest = m >> (k + 1);
+    const int len = rest ? __ffsll((long long)rest) : nk - k;
+    bulk_load(dst + k * 128, plane + (long long)row0 * rowpitch + k * 64, (uint32_t)len * 128u, bar);
+  }
+  if (s1) {
+    const int k = lane + 32;
+    const unsigned long long rest = k + 1 < 64 ? m >> (k + 1) : 0ull;
+    const int len = rest ? __ffsll((long long)rest) : nk - k;
+    bulk_load(dst + k * 128, plane + (long long)row1 * rowpitch + k * 64, (uint32_t)len * 128u, bar);
+  }
+}
+
+__device__ __forceinline__ void decode_self_attn_runs(const DecAttnArgs& a, int first, int stride, int items,
+                                                      uint8_t* kv_smem, bf16* q_stage, uint64_t* bar_k, uint64_t* bar_v,
+                                                      uint32_t* par_k, uint32_t* par_v, int lane) {
+  constexpr int QP = 72;
+  const int nk = a.n_keys;
+  const uint32_t kv_base = smem_u32(kv_smem);
+  const long long rowpitch = (long long)a.T * 2 * a.H * HD;
+  const int plane = a.T * HD;                      // elements per (head, K or V) plane
+  int i = first;
+  if (i >= items) return;
+  {   // V rows nk .. next multiple of 16 take part in the P.V MMAs with P = 0: they must be finite (never overwritten)
+    const int pad_rows = ((nk + 15) & ~15) - nk;
+    for (int t = lane; t < pad_rows * 8; t += 32)
+      *reinterpret_cast<uint4*>(kv_smem + 8192 + (nk + (t >> 3)) * 128 + ((t & 7) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();                             // this warp's earlier generic use of the stage precedes the copies
+  __syncwarp();
+  int row0, row1;
+  decode_attn_rows(a, i / a.H, lane, &row0, &row1);
+  {
+    const bf16* hb = a.kc + (long long)(i % a.H) * 2 * plane;
+    attn_issue_runs(hb, rowpitch, nk, row0, row1, kv_smem, bar_k, lane);
+    attn_issue_runs(hb + plane, rowpitch, nk, row0, row1, kv_smem + 8192, bar_v, lane);
+  }
+  while (true) {
+    const int r = i / a.H, h = i % a.H;
+    const int inext = i + stride;
+    const bool has_next = inext < items;
+    int nrow0 = 0, nrow1 = 0;
+    if (has_next) decode_attn_rows(a, inext / a.H, lane, &nrow0, &nrow1);
+    // query row -> bf16 stage row 0 (pre-scaled: 1/8 is exact), rows 1..7 zero: 64 chunks, 2 per lane
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int id = lane + t * 32;
+      const int rr = id >> 3, c8 = (id & 7) * 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      if (rr == 0) {
+        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= a.scale;
+      }
+      store8(q_stage + rr * QP + c8, f);
+    }
+    __syncwarp();
+    mbar_wait(bar_k, *par_k);
+    *par_k ^= 1;
+    uint32_t pa[8];
+    float inv;
+    attn_qk_softmax(kv_base, q_stage, nk, lane, pa, &inv);
+    fence_proxy_async();                            // generic reads of the K half precede the next item's bulk copies
+    __syncwarp();
+    const bf16* hb = a.kc + (long long)(inext % a.H) * 2 * plane;
+    if (has_next) attn_issue_runs(hb, rowpitch, nk, nrow0, nrow1, kv_smem, bar_k, lane);
+    mbar_wait(bar_v, *par_v);
+    *par_v ^= 1;
+    attn_pv_store(a, kv_base, nk, pa, inv, r, h, lane);
+    fence_proxy_async();
+    __syncwarp();
+    if (!has_next) break;
+    attn_issue_runs(hb + plane, rowpitch, nk, nrow0, nrow1, kv_smem + 8192, bar_v, lane);
+    i = inext;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cross-attention item on pre-packed K|V stage images: the whole 16 KB stage arrives with ONE bulk copy (vs 800
 // 16-byte cp.async), the query rows of the item are loaded while it is in flight.
 // ---------------------------------------------------------------------------------------------

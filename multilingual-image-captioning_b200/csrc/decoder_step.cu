@@ -41,9 +41,13 @@ constexpr int NACC = 1;                       // (4 independent accumulators per
                                               // chain is not what bounds a unit - the L2 -> SM operand stream is)
 constexpr int TMEM_COLS = 2 * NACC * BN;      // double-buffered
 constexpr int VEC_SCRATCH = EW * 2048;        // per-warp attention scratch: queries [4, 64] f32, numerators [64], spare
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + VEC_SCRATCH + 256 + 1024;
+constexpr int BAR_BYTES = 512;               // 2*STAGES + 4 + 2*EW mbarriers + the TMEM base word
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + VEC_SCRATCH + BAR_BYTES + 1024;
 
 enum { PH_GEMM_STORE = 0, PH_GEMM_RED = 1, PH_LN = 2, PH_ATTN = 3 };
+// barrier state (256 uint32, zero before the first launch): [0] arrival counter of the counter barrier,
+// [SYNC_EPOCH] launch-epoch base of the flag barrier, [SYNC_FLAGS + cta] phases completed by each CTA (+ epoch base)
+constexpr int SYNC_EPOCH = 32, SYNC_FLAGS = 64, OPT_NO_WRITER_FENCE = 1, OPT_FLAG_BARRIER = 2;
 
 struct Phase {
   int kind;
@@ -54,12 +58,13 @@ struct Phase {
   int act;                        // GEMM_STORE: activation after bias
   int col_split;                  // GEMM_STORE: columns >= col_split go to out2 (the K|V cache slot of this step)
   int out_tiled_kb;               // GEMM_STORE: > 0 -> `out` is a tile-image buffer with that many k blocks per row
-  int cache_swizzle;              // GEMM_STORE: cache rows are stored in the attention stage's chunk order (c ^ (pos & 7))
+  int cache_T;                    // GEMM_STORE with out2: cache length (positions per head plane)
   const float* bias;              // GEMM_STORE: bias[N];  LN: bias of the GEMM that produced acc
   void* out;                      // GEMM_STORE: bf16 [R, ldo];  GEMM_RED / LN: fp32 accumulator [R, ldo]
   long long ldo;
-  bf16* out2;                     // cache layer base; element (row, pos, c) at row*ldo2 + pos*pos_pitch + c
-  long long ldo2, pos_pitch;
+  bf16* out2;                     // cache layer base, head-major: element (row, head, K|V, pos, c) at
+                                  // row*ldo2 + (head*2 + kv)*cache_T*64 + pos*64 + chunk-swizzled c (decode_device.cuh)
+  long long ldo2;
   // ---- LN: x += acc + bias; y = LN(x); acc = 0
   bf16* x;
   bf16* y;
@@ -80,6 +85,9 @@ struct StepArgs {
   int pos;                        // position being decoded (cache slot written, n_keys = pos + 1)
   unsigned int* sync;             // grid-barrier arrival counter (zero before the launch; the kernel re-zeroes it)
   unsigned long long* prof;       // optional [num_phases, gridDim] globaltimer stamps of each CTA's phase arrival
+  const int* active;              // optional device flag of the search loop (beam_cond / greedy_cond): 0 = every
+                                  // hypothesis finished -> the whole step is skipped (the while_loop has ended)
+  int opts;                       // bit 0: no writer-side generic->async proxy fence (readers fence after their acquire)
 };
 
 // ---- The role loops below are written for INSTRUCTION COUNT: each is a single thread (or a single warp per work
@@ -125,14 +133,22 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint64_t* attn_bar = bars + 2 * STAGES + 4;       // one per vector warp (self-attention bulk copies)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EW);
+  uint64_t* attn_bar = bars + 2 * STAGES + 4;       // per vector warp: K operand / whole cross-attention stage
+  uint64_t* attn_bar_v = attn_bar + EW;             // per vector warp: V operand of the self-attention pipeline
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * EW);
+  static_assert((2 * STAGES + 4 + 2 * EW) * 8 + 4 <= BAR_BYTES, "barrier block overflows its shared-memory slot");
 
+  // the search loop has terminated (device-side while_loop condition): nothing to decode.  The flag was written by
+  // an earlier kernel of the stream, so every thread of every CTA reads the same value.
+  if (args.active != nullptr && *args.active == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int P = args.num_phases;
   const Phase* phases = args.phases;
   const int m_tiles = (args.R + BM - 1) / BM;
+  const bool flag_bar = (args.opts & OPT_FLAG_BARRIER) != 0;
+  const unsigned int* flags = args.sync + SYNC_FLAGS;
+  const unsigned int epoch = flag_bar ? ld_relaxed_gpu(args.sync + SYNC_EPOCH) : 0u;   // set by the previous launch
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EW);
     }
-    for (int i = 0; i < EW; ++i) mbar_init(&attn_bar[i], 1);
+    for (int i = 0; i < 2 * EW; ++i) mbar_init(&attn_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -181,20 +197,25 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {
-      // ===================== activation producer: gated on the grid barrier of the previous phase ==========
-      int slot = 0, round = 0;
-      for (int p = 0; p < P; ++p) {
-        const Phase& ph = phases[p];
-        if (ph.kind > PH_GEMM_RED) continue;
-        const int units = m_tiles * ph.n_tiles * ph.split_k;
-        if (cta >= units) continue;
-        Unit t = unit_of(ph, cta, m_tiles);              // address arithmetic of the first unit before the wait
-        if (p > 0) {
+    // ===================== activation producer: gated on the grid barrier of the previous phase ==========
+    // (lane 0 issues the copies; with the flag barrier the whole warp polls the per-CTA flags)
+    int slot = 0, round = 0;
+    for (int p = 0; p < P; ++p) {
+      const Phase& ph = phases[p];
+      if (ph.kind > PH_GEMM_RED) continue;
+      const int units = m_tiles * ph.n_tiles * ph.split_k;
+      if (cta >= units) continue;
+      Unit t = unit_of(ph, cta, m_tiles);              // address arithmetic of the first unit before the wait
+      if (p > 0) {
+        if (flag_bar) {
+          flags_wait_warp(flags, G, epoch + (unsigned int)p, lane);
+        } else if (lane == 0) {
           while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
           fence_acquire_gpu();
-          fence_proxy_async_global();
         }
+        if (lane == 0) fence_proxy_async_global();
+      }
+      if (lane == 0) {
         const bool trc = args.prof && cta == TRACE_CTA && p == TRACE_PHASE;
         if (trc) args.prof[(long long)P * G + 129] = gtime();
         for (int u = cta; u < units; u += G) {
@@ -214,6 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -271,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
     const int vt = threadIdx.x - 128;          // 0..255 among the vector warps
     const bool leader = threadIdx.x == 128;
     uint32_t it = 0;
-    uint32_t attn_parity = 0;                  // phase parity of this warp's attention-stage barrier
+    uint32_t attn_parity = 0, attn_parity_v = 0;  // phase parities of this warp's attention-stage barriers
     for (int p = 0; p < P; ++p) {
       const Phase& ph = phases[p];
       if (ph.kind <= PH_GEMM_RED) {
@@ -279,7 +301,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         if (cta >= units && p > 0) {
           // no work here: still do not arrive for phase p before phase p-1 is complete everywhere, so that
           // (arrivals / G) counts whole phases (CTAs with work inherit this from their gated activation loads)
-          if (leader) {
+          // (flag barrier: a CTA's word counts ITS completed phases, so an idle CTA may run ahead)
+          if (leader && !flag_bar) {
             while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
             fence_acquire_gpu();
           }
@@ -299,9 +322,15 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 128] = gtime();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * (NACC * BN) + half * 32;
           const bool to_cache = col0 >= ph.col_split;
-          bf16* dst = to_cache ? ph.out2 + (long long)row * ph.ldo2 + (long long)args.pos * ph.pos_pitch +
-                                     (col0 - ph.col_split)
-                               : reinterpret_cast<bf16*>(ph.out) + (long long)row * ph.ldo + col0;
+          bf16* dst = reinterpret_cast<bf16*>(ph.out) + (long long)row * ph.ldo + col0;
+          int cache_chunk0 = 0;
+          if (to_cache) {
+            // this position's K|V row of (row, head): 32 of its 64 values, as 4 chunks swizzled by the position
+            const int kvcol = col0 - ph.col_split, dm = ph.col_split;          // col_split == d_model
+            const int kv = kvcol >= dm, head = (kvcol - kv * dm) >> 6;
+            dst = ph.out2 + (long long)row * ph.ldo2 + (long long)(head * 2 + kv) * ph.cache_T * 64 + args.pos * 64;
+            cache_chunk0 = (kvcol & 63) >> 3;
+          }
           float* racc = reinterpret_cast<float*>(ph.out) + (long long)row * ph.ldo + col0;
           float v[32];
           tmem_ld_32x32(taddr, v);
@@ -330,8 +359,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
                 }
                 if (!to_cache && ph.out_tiled_kb)
                   store8(reinterpret_cast<bf16*>(ph.out) + tiled_off(row, col0 + j, ph.out_tiled_kb), v + j);
-                else if (to_cache && ph.cache_swizzle)     // col0 % 32 == 0: chunk index (j >> 3) | (col0 & 32) >> 3
-                  store8(dst - (col0 & 63) + ((((((col0 & 63) + j) >> 3) ^ (args.pos & 7))) << 3), v + j);
+                else if (to_cache)
+                  store8(dst + (((cache_chunk0 + (j >> 3)) ^ (args.pos & 7)) << 3), v + j);
                 else
                   store8(dst + j, v + j);
               }
@@ -341,11 +370,17 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       } else {
         // vector phase: inputs come from earlier phases of other CTAs
         if (p > 0) {
-          if (leader) {
+          if (flag_bar) {
+            if (ew == 0) flags_wait_warp(flags, G, epoch + (unsigned int)p, lane);
+          } else if (leader) {
             while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
             fence_acquire_gpu();
           }
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+          // attention operands arrive through the async proxy (bulk copies) but were written with generic stores by
+          // other CTAs (this position's K|V, the cross-attention queries' accumulator is read generically): order
+          // the acquired writes before this thread's copies
+          if (ph.kind == PH_ATTN) fence_proxy_async_global();
         }
         if (ph.kind == PH_LN) {
           // x += acc + bias; y = LN(x); acc = 0.  Two rows per CTA at a time, 128 vector threads (8 columns each)
@@ -409,7 +444,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
           const bool tra = args.prof && cta == TRACE_CTA && ew == 0 && p == 1 + 1 + 11 * 5;
           if (tra && lane == 0) args.prof[(long long)P * G + 169] = gtime();
           if (ph.keys_from_pos && a.q != nullptr) {
-            decode_self_attn_pipelined(a, gw, nw, items, kv_stage, reinterpret_cast<bf16*>(q_smem), lane);
+            decode_self_attn_runs(a, gw, nw, items, kv_stage, reinterpret_cast<bf16*>(q_smem), &attn_bar[ew],
+                                  &attn_bar_v[ew], &attn_parity, &attn_parity_v, lane);
           } else if (a.kv_tiles != nullptr) {
             for (int i = gw; i < items; i += nw)
               decode_cross_attn_packed(a, i / a.H, i % a.H, kv_stage, reinterpret_cast<bf16*>(q_smem), &attn_bar[ew],
@@ -430,17 +466,25 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 130] = gtime();
       // only phases whose output is fetched by bulk copies (tile-image activations) or that used the ring as scratch
       // need the generic -> async proxy fence (0.6 us); split-K reductions and the q|k|v store feed generic loads
-      if (ph.kind == PH_LN || ph.kind == PH_ATTN || (ph.kind == PH_GEMM_STORE && ph.out_tiled_kb)) fence_proxy_async_global();
+      if (!(args.opts & 1) &&
+          (ph.kind == PH_LN || ph.kind == PH_ATTN || (ph.kind == PH_GEMM_STORE && (ph.out_tiled_kb || ph.out2))))
+        fence_proxy_async_global();
       if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 131] = gtime();
       // ---- grid barrier arrival: this CTA's writes of phase p are done.  The leader's release (gpu scope) is
       // cumulative over the other warps' writes, which precede it through the CTA barrier.
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (leader) {
         if (args.prof) args.prof[(long long)p * G + cta] = gtime();
-        const unsigned int old = atom_add_release_gpu(args.sync, 1u);
-        if (p == P - 1 && old == (unsigned int)P * (unsigned int)G - 1u) {
-          __threadfence();
-          *reinterpret_cast<volatile unsigned int*>(args.sync) = 0u;     // last arrival of the launch: re-arm
+        if (flag_bar) {
+          st_release_gpu(args.sync + SYNC_FLAGS + cta, epoch + (unsigned int)p + 1u);
+          // CTA 0 got here only after every CTA completed phase P-2, i.e. long after all of them read the epoch
+          if (p == P - 1 && cta == 0) *reinterpret_cast<volatile unsigned int*>(args.sync + SYNC_EPOCH) = epoch + (unsigned int)P;
+        } else {
+          const unsigned int old = atom_add_release_gpu(args.sync, 1u);
+          if (p == P - 1 && old == (unsigned int)P * (unsigned int)G - 1u) {
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int*>(args.sync) = 0u;     // last arrival of the launch: re-arm
+          }
         }
       }
     }
@@ -460,6 +504,22 @@ __global__ void __launch_bounds__(THREADS, 1) barrier_bench_kernel(unsigned int*
   const int G = gridDim.x;
   if (threadIdx.x < 128) return;
   const bool leader = threadIdx.x == 128;
+  if (variant == 4) {          // per-CTA flag words + launch epoch (OPT_FLAG_BARRIER)
+    const unsigned int epoch = ld_relaxed_gpu(sync + SYNC_EPOCH);
+    const int w = (threadIdx.x - 128) >> 5, lane = threadIdx.x & 31;
+    for (int p = 0; p < n; ++p) {
+      if (p > 0) {
+        if (w == 0) flags_wait_warp(sync + SYNC_FLAGS, G, epoch + (unsigned int)p, lane);
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+      if (leader) {
+        st_release_gpu(sync + SYNC_FLAGS + blockIdx.x, epoch + (unsigned int)p + 1u);
+        if (p == n - 1 && blockIdx.x == 0) *reinterpret_cast<volatile unsigned int*>(sync + SYNC_EPOCH) = epoch + (unsigned int)n;
+      }
+    }
+    return;
+  }
   for (int p = 0; p < n; ++p) {
     if (p > 0) {
       if (leader || variant == 3) {
@@ -648,12 +708,12 @@ extern "C" int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_dec
     p[0].col_split = d;
     p[0].out2 = (bf16*)w.self_kv;
     p[0].ldo2 = (long long)cache_len * 2 * d;
-    p[0].pos_pitch = 2 * d;
+    p[0].cache_T = cache_len;
     // 1: cached self-attention through the ancestor table
     p[1].kind = PH_ATTN;
     p[1].keys_from_pos = 1;
     DecAttnArgs& sa = p[1].attn;
-    sa.q = (const bf16*)buf->q; sa.ldq = d; sa.kc = (const bf16*)w.self_kv; sa.vc = (const bf16*)w.self_kv + d;
+    sa.q = (const bf16*)buf->q; sa.ldq = d; sa.kc = (const bf16*)w.self_kv; sa.vc = nullptr;   // head-major cache
     sa.ldkv = 2 * d; sa.anc = buf->ancestors; sa.T = cache_len; sa.n_keys = 1; sa.rows_per_kv = 1;
     sa.o = (bf16*)buf->o_tiles; sa.ldo = d; sa.R = R; sa.H = heads; sa.scale = scale; sa.q_acc = nullptr;
     sa.q_bias = nullptr; sa.o_tiled_kb = d / BK; sa.kv_tiles = nullptr; sa.kv_tiles_stride = 0;
@@ -692,7 +752,8 @@ extern "C" int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_dec
 }
 
 extern "C" int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, int pos,
-                                unsigned int* sync_counter, unsigned long long* phase_times) {
+                                unsigned int* sync_counter, unsigned long long* phase_times, const int* active,
+                                int opts) {
   MIC_CHECK_ARG(plan_dev && sync_counter && num_layers > 0 && R > 0 && pos >= 0, "decoder step: bad argument");
   static bool attr_set = false;
   if (!attr_set) {
@@ -706,6 +767,8 @@ extern "C" int mic_decoder_step(void* stream, const void* plan_dev, int num_laye
   a.pos = pos;
   a.sync = sync_counter;
   a.prof = phase_times;
+  a.active = active;
+  a.opts = opts;
   // every CTA must be resident at once (grid barrier): one CTA per SM (214 KB of shared memory each), grid = #SMs
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(mic_num_sms());

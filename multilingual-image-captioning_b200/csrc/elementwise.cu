@@ -624,13 +624,17 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const int* __restrict__ mas
 
 // ---------------------------------------------------------------------------------------------
 // AdamW (optax 0.0.9 chain: scale_by_adam -> add_decayed_weights -> scale(-lr)), flat fp32 state,
-// bf16 shadow refresh.  hp[] lives in device memory so a captured graph can be replayed:
-//   hp = {lr, b1, b2, eps, wd, 1/(1-b1^t), 1/(1-b2^t), grad_scale}
+// bf16 shadow refresh.  The step's scalars are kernel ARGUMENTS (by value): the update runs outside the captured
+// forward/backward graph, and a pinned staging buffer would be overwritten by a host that runs steps ahead.
+//   c1 = 1/(1-b1^t), c2 = 1/(1-b2^t), gs = gradient scale (1/world)
 // ---------------------------------------------------------------------------------------------
+struct AdamHyper {
+  float lr, b1, b2, eps, wd, c1, c2, gs;
+};
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-             bf16* __restrict__ shadow, const float* __restrict__ hp, long long n) {
-  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], c1 = hp[5], c2 = hp[6], gs = hp[7];
+             bf16* __restrict__ shadow, const AdamHyper hp, long long n) {
+  const float lr = hp.lr, b1 = hp.b1, b2 = hp.b2, eps = hp.eps, wd = hp.wd, c1 = hp.c1, c2 = hp.c2, gs = hp.gs;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -864,12 +868,14 @@ extern "C" int mic_ce_finalize(void* stream, const float* pmax, const float* psu
   return MIC_OK;
 }
 
-extern "C" int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* shadow_bf16,
-                         const float* hyper_dev, long long n) {
+extern "C" int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* shadow_bf16, long long n,
+                         float lr, float b1, float b2, float eps, float weight_decay, float bias_corr1,
+                         float bias_corr2, float grad_scale) {
+  const AdamHyper hyper = {lr, b1, b2, eps, weight_decay, bias_corr1, bias_corr2, grad_scale};
   MIC_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
                     ((uintptr_t)g & 15) == 0,
                 "adamw: state pointers must be 16-byte aligned");
-  adamw_kernel<<<grid_for(n / 4 + 1, 256, 16), 256, 0, STREAM>>>(p, m, v, g, (bf16*)shadow_bf16, hyper_dev, n);
+  adamw_kernel<<<grid_for(n / 4 + 1, 256, 16), 256, 0, STREAM>>>(p, m, v, g, (bf16*)shadow_bf16, hyper, n);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

@@ -498,6 +498,9 @@ struct EpiSearchParams {
   // the row's pair (upper_val, upper_idx) - the 8th best of the first pass - are considered; null = first pass
   const float* upper_val;
   const int* upper_idx;
+  // device flag of the search loop's while_loop condition (null = always run): 0 -> the kernel returns at once, the
+  // (stale) partial lists are ignored by the equally gated bookkeeping kernels
+  const int* active;
 };
 
 // The launcher sizes the grid as a multiple of num_m_blocks with group_m == num_m_blocks, so every CTA
@@ -651,6 +654,9 @@ struct EpiSearch {
 
 struct EpiSearchPacked : EpiSearch {};
 template <class Epi> struct PackedOperands { static constexpr bool value = false; };
+template <class Epi> struct IsSearchEpi { static constexpr bool value = false; };
+template <> struct IsSearchEpi<EpiSearch> { static constexpr bool value = true; };
+template <> struct IsSearchEpi<EpiSearchPacked> { static constexpr bool value = true; };
 template <> struct PackedOperands<EpiSearchPacked> { static constexpr bool value = true; };
 
 // --------------------------------------------------------------------------------------------
@@ -662,6 +668,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d2,
             const Shape shape, const typename Epi::Params ep) {
   typedef Cfg<BN, Epi::NBUF, Epi::EW> C;
+  if constexpr (IsSearchEpi<Epi>::value) {
+    if (ep.active != nullptr && *ep.active == 0) return;     // uniform over the grid: written by an earlier kernel
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // 1024B alignment for SWIZZLE_128B

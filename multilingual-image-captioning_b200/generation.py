@@ -90,6 +90,21 @@ def decode_step(engine, cache: DecodeCache, tokens, pos: int):
     return a
 
 
+def fused_cache_rowmajor(engine, cache: DecodeCache):
+    """The self-attention cache of the FUSED path, converted to the per-op path's [layer, row, pos, k|v] layout
+    (tests / debugging).  The persistent kernel keeps it head-major — [row][head][K plane | V plane][pos][64], the
+    16-byte chunk c of a (pos) row stored at c ^ (pos & 7) — so that one beam's K (or V) history of a head is a
+    few contiguous runs that bulk copies fetch (csrc/decode_device.cuh: decode_self_attn_runs)."""
+    t = engine.t
+    L, R, T, H = t.decoder_layers, cache.rows, cache.T, t.decoder_attention_heads
+    kv = cache.self_kv.reshape(L, R, H, 2, T, 8, 8)
+    pos = torch.arange(T, device=kv.device)
+    src = (torch.arange(8, device=kv.device)[None, :] ^ (pos[:, None] & 7))          # [T, 8]: stored chunk of logical c
+    idx = src[None, None, None, None, :, :, None].expand(L, R, H, 2, T, 8, 8)
+    logical = torch.gather(kv, 5, idx).reshape(L, R, H, 2, T, 64)
+    return logical.permute(0, 1, 4, 3, 2, 5).reshape(L, R, T, 2 * H * 64).contiguous()
+
+
 def _aligned(engine, name, nbytes, align=1024):
     """Cached uint8 device buffer with an aligned start (tile-image buffers are bulk-copy sources)."""
     raw = engine.bufs.get(name, (nbytes + align,), torch.uint8)
@@ -141,7 +156,7 @@ def _fused_plan(engine, cache: DecodeCache, tiled_out=False):
     lstruct = ops.decoder_layers_struct(layers)
     plan = torch.empty(ops.decoder_plan_bytes(L) + 128, dtype=torch.uint8, device=engine.dev)
     plan = plan[(-plan.data_ptr()) % 128:]
-    sync = torch.zeros(1, dtype=I32, device=engine.dev)
+    sync = torch.zeros(256, dtype=I32, device=engine.dev)
     for n in ("a_tiles", "o_tiles", "g_tiles", "h_out_tiles"):
         if bufs[n] is not None:
             bufs[n].zero_()                                   # rows beyond R of the last row tile stay finite
@@ -168,7 +183,7 @@ def fused_prepare(engine, cache: DecodeCache, packed_search=False):
     return fp
 
 
-def decode_step_fused(engine, cache: DecodeCache, tokens, pos: int, fp=None):
+def decode_step_fused(engine, cache: DecodeCache, tokens, pos: int, fp=None, active=None):
     """decode_step with all decoder layers in ONE persistent kernel (csrc/decoder_step.cu)."""
     t, ps = engine.t, engine.ps
     assert t.pre_layernorm and t.final_layer_norm, "fused cached decode is wired for the pre-LN (mBART) decoder"
@@ -176,7 +191,7 @@ def decode_step_fused(engine, cache: DecodeCache, tokens, pos: int, fp=None):
         fp = fused_prepare(engine, cache)
     ops.embed_ln_fwd(tokens, None, 1, pos + t.position_offset, ps.w("shared"), ps.w("d.pos"), engine.emb_scale,
                      ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), t.layer_norm_eps, None, fp["bufs"]["x"])
-    ops.decoder_step(fp["plan"], t.decoder_layers, cache.rows, pos, fp["sync"])
+    ops.decoder_step(fp["plan"], t.decoder_layers, cache.rows, pos, fp["sync"], active=active)
     return fp["bufs"]["h_out_tiles"] if fp["bufs"]["h_out_tiles"] is not None else fp["bufs"]["h_out"]
 
 
@@ -190,6 +205,13 @@ def _search_ws(engine, R, cand_per_row=8):
             "last_val": b.get("gen.last_val", (R,), F32), "last_idx": b.get("gen.last_idx", (R,), I32)}
 
 
+def _min_length_applies(cur_len, min_length):
+    """FlaxMinLengthLogitsProcessor (transformers@0085e712 generation_flax_logits_process.py, risk U4 [MEMORY]):
+    `apply_penalty = 1 - clip(cur_len - min_length, 0, 1)` — EOS is masked while cur_len <= min_length, one step
+    longer than the PyTorch processor's `cur_len < min_length`."""
+    return 1 - min(max(cur_len - min_length, 0), 1) == 1
+
+
 def _forced_token(cur_len, max_length, forced_bos, forced_eos):
     """FlaxForcedBOS (cur_len == 1) then FlaxForcedEOS (cur_len == max_length-1): the later processor wins."""
     f = -1
@@ -200,13 +222,15 @@ def _forced_token(cur_len, max_length, forced_bos, forced_eos):
     return f
 
 
-def _step(engine, cache, tokens, pos):
+def _step(engine, cache, tokens, pos, active=None):
+    """`active` = the device-side while_loop condition: once it is 0 the persistent decoder step and the lm_head
+    search return immediately (the reference's loop would have ended, generation_clip_vision_utils.py:798-820)."""
     if cache.fused is not None:
-        return decode_step_fused(engine, cache, tokens, pos, cache.fused)
+        return decode_step_fused(engine, cache, tokens, pos, cache.fused, active=active)
     return decode_step(engine, cache, tokens, pos)
 
 
-def _lm_head_search(engine, cache, hf, mask_token, ws):
+def _lm_head_search(engine, cache, hf, mask_token, ws, active=None):
     """lm_head + log-softmax partials + per-row candidates.  8 candidates per row cover 2*num_beams for <= 4 beams;
     5..8 beams run the search a second time restricted to what ranks after the first pass's 8th (exact: both passes
     compute bit-identical logits)."""
@@ -215,9 +239,9 @@ def _lm_head_search(engine, cache, hf, mask_token, ws):
     for i in range(passes):
         if cache.fused is not None and "e_tiles" in cache.fused:
             ops.lm_head_search_packed(hf, cache.fused["e_tiles"], ps.f("flb"), int(mask_token), cache.rows, t.vocab_size,
-                                      t.d_model, ws, second_pass=i == 1)
+                                      t.d_model, ws, second_pass=i == 1, active=active)
         else:
-            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws, second_pass=i == 1)
+            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws, second_pass=i == 1, active=active)
         ops.search_merge(ws, cache.rows, second_pass=i == 1)
 
 
@@ -253,10 +277,10 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
             forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
             last = cur_len == Lmax - 1
             if not (last and forced >= 0):
-                hf = _step(engine, cache, st["next_token"], cur_len - 1)
+                hf = _step(engine, cache, st["next_token"], cur_len - 1, active)
             if forced < 0:
-                mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
-                _lm_head_search(engine, cache, hf, mt, ws)
+                mt = eos_token_id if (mask_eos and _min_length_applies(cur_len, min_length)) else -1
+                _lm_head_search(engine, cache, hf, mt, ws, active)
             ops.greedy_step(ws, st, forced, R, Lmax, cur_len, eos_token_id, pad_token_id)
             ops.greedy_cond(st, R, cur_len + 1, Lmax)
         return {"sequences": st["sequences"]}
@@ -273,10 +297,10 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
         forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
         last = cur_len == Lmax - 1
         if not (last and forced >= 0):
-            hf = _step(engine, cache, st["next_token"], cur_len - 1)
+            hf = _step(engine, cache, st["next_token"], cur_len - 1, active)
         if forced < 0:
-            mt = eos_token_id if (mask_eos and cur_len < min_length) else -1
-            _lm_head_search(engine, cache, hf, mt, ws)
+            mt = eos_token_id if (mask_eos and _min_length_applies(cur_len, min_length)) else -1
+            _lm_head_search(engine, cache, hf, mt, ws, active)
         ops.beam_step(ws, st, forced, B, K, Lmax, V, cur_len, eos_token_id, early_stopping, length_penalty)
         ops.beam_cond(st, B, K, cur_len + 1, Lmax, length_penalty, early_stopping)
     out_seq = torch.empty((B, Lmax), dtype=I32, device=dev)

@@ -108,10 +108,10 @@ def pack_kmajor_tiles(src, tile_rows, out):
     _call("mic_pack_kmajor_tiles", _p(src), _ld(src), rows, K, tile_rows, _p(out))
 
 
-def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws, second_pass=False):
+def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws, second_pass=False, active=None):
     _call("mic_lm_head_search_packed", _p(h_tiles), _p(e_tiles), _p(bias), mask_token, M, V, K, _p(ws["pmax"]),
           _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]), _p(ws["last_val"]) if second_pass else None,
-          _p(ws["last_idx"]) if second_pass else None)
+          _p(ws["last_idx"]) if second_pass else None, _p(active))
 
 
 def lm_head_ce_stats(h, emb, bias, labels, ws, logits_out=None):
@@ -145,12 +145,12 @@ def lm_head_ce_grad(h, emb, bias, labels, ws, conf, low, dlogits):
           _p(ws["row_w"]), float(conf), float(low), M, V, K, _p(dlogits), _ld(dlogits))
 
 
-def lm_head_search(h, emb, bias, mask_token, ws, second_pass=False):
+def lm_head_search(h, emb, bias, mask_token, ws, second_pass=False, active=None):
     M, K = h.shape
     V = emb.shape[0]
     _call("mic_lm_head_search", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), int(mask_token), M, V, K,
           _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]),
-          _p(ws["last_val"]) if second_pass else None, _p(ws["last_idx"]) if second_pass else None)
+          _p(ws["last_val"]) if second_pass else None, _p(ws["last_idx"]) if second_pass else None, _p(active))
 
 
 def search_merge(ws, R, second_pass=False):
@@ -233,8 +233,12 @@ def decoder_pack_cross_kv(enc_kv, B, S, num_layers, heads, d_model, out):
     _call("mic_decoder_pack_cross_kv", _p(enc_kv), _ld(enc_kv), B, S, num_layers, heads, d_model, _p(out))
 
 
-def decoder_step(plan, num_layers, R, pos, sync, phase_times=None):
-    _call("mic_decoder_step", _p(plan), num_layers, R, pos, _p(sync), _p(phase_times))
+DECODER_STEP_OPTS = [int(__import__("os").environ.get("MIC_DECODER_OPTS", "0"))]     # tuning switches (include/mic_b200.h)
+
+
+def decoder_step(plan, num_layers, R, pos, sync, phase_times=None, active=None, opts=None):
+    _call("mic_decoder_step", _p(plan), num_layers, R, pos, _p(sync), _p(phase_times), _p(active),
+          DECODER_STEP_OPTS[0] if opts is None else int(opts))
 
 
 def launch_options(pdl=-1, gemm_b_static=-1):
@@ -320,8 +324,10 @@ def drop_cls_rows(d_emb, out, B, S):
     return out
 
 
-def adamw(p, m, v, g, shadow, hyper_dev):
-    _call("mic_adamw", _p(p), _p(m), _p(v), _p(g), _p(shadow), _p(hyper_dev), p.numel())
+def adamw(p, m, v, g, shadow, lr, b1, b2, eps, weight_decay, bias_corr1, bias_corr2, grad_scale):
+    """The eight scalars are passed by value (kernel arguments fixed at enqueue time)."""
+    _call("mic_adamw", _p(p), _p(m), _p(v), _p(g), _p(shadow), p.numel(), float(lr), float(b1), float(b2), float(eps),
+          float(weight_decay), float(bias_corr1), float(bias_corr2), float(grad_scale))
 
 
 def cast_f32_to_bf16(src, dst):

@@ -54,8 +54,6 @@ class TrainState:
         self.learning_rate_fn = learning_rate_fn
         self.b1, self.b2, self.eps, self.weight_decay = b1, b2, eps, weight_decay
         self.step = 0
-        self.hp_host = torch.zeros(8, dtype=F32).pin_memory()
-        self.hp_dev = torch.zeros(8, dtype=F32, device=self.store.device)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_elems = max(int(bucket_bytes) // 4, 1)
         self.metrics_buf = torch.zeros(2, dtype=F32, device=self.store.device)
@@ -64,7 +62,6 @@ class TrainState:
         # one fresh mask per step and per rank (dropout_rng split / shard_prng_key, main.py:251,686)
         self.dropout = model.config.mbart_config.dropout if dropout is None else float(dropout)
         self.dropout_seed = int(dropout_seed)
-        self.seed_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.rank = dist.get_rank() if self.world > 1 else 0
 
     @classmethod
@@ -112,24 +109,19 @@ class TrainState:
         count = self.step
         t = count + 1
         lr = float(self.learning_rate_fn(count))
-        self.hp_host[0] = lr
-        self.hp_host[1] = self.b1
-        self.hp_host[2] = self.b2
-        self.hp_host[3] = self.eps
-        self.hp_host[4] = self.weight_decay
-        self.hp_host[5] = 1.0 / (1.0 - self.b1 ** t)
-        self.hp_host[6] = 1.0 / (1.0 - self.b2 ** t)
-        self.hp_host[7] = 1.0 / self.world
-        self.hp_dev.copy_(self.hp_host, non_blocking=True)
+        # scalars by value: the host may run many steps ahead of the stream (no per-step sync), so nothing the
+        # enqueued update reads may live in a buffer the next step rewrites
+        hp = (lr, self.b1, self.b2, self.eps, self.weight_decay, 1.0 / (1.0 - self.b1 ** t), 1.0 / (1.0 - self.b2 ** t),
+              1.0 / self.world)
         s = self.store
         if segments is None:
-            ops.adamw(s.master, s.adam_m, s.adam_v, s.grad, s.shadow, self.hp_dev)
+            ops.adamw(s.master, s.adam_m, s.adam_v, s.grad, s.shadow, *hp)
         else:
             cur = torch.cuda.current_stream()
             for lo, hi, ev in segments:
                 if ev is not None:
                     cur.wait_event(ev)
-                ops.adamw(s.master[lo:hi], s.adam_m[lo:hi], s.adam_v[lo:hi], s.grad[lo:hi], s.shadow[lo:hi], self.hp_dev)
+                ops.adamw(s.master[lo:hi], s.adam_m[lo:hi], s.adam_v[lo:hi], s.grad[lo:hi], s.shadow[lo:hi], *hp)
         self.step = t
         return lr
 
@@ -195,8 +187,7 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
     eng.dropout_p = state.dropout
     if state.dropout > 0.0:
         mix = (state.dropout_seed * 1000003 + state.step * 7919 + state.rank * 104729 + 12345) & 0x3FFFFFFF
-        state.seed_host[0] = mix
-        eng.drop_seed.copy_(state.seed_host, non_blocking=True)
+        eng.drop_seed.fill_(mix)      # scalar travels as a kernel argument (fixed at enqueue time; the graph reads the tensor)
     sb = _static_batch(state, batch)
     args = (sb["pixel_values"], sb["decoder_input_ids"], sb["attention_mask"], sb["input_ids"])
     ls = (label_smoothing_factor, state.dropout)

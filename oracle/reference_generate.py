@@ -40,12 +40,13 @@ def log_softmax(x: np.ndarray) -> np.ndarray:
 def apply_processors(scores: np.ndarray, cur_len: int, *, min_length, eos_token_id, forced_bos_token_id,
                      forced_eos_token_id, max_length) -> np.ndarray:
     """`_get_logits_processor` (:368-420) order: MinLength, ForcedBOS, ForcedEOS.
-    FlaxMinLength: where(cur_len - min_length < 0) scores[:, eos] = -inf
+    FlaxMinLength: apply_penalty = 1 - clip(cur_len - min_length, 0, 1) -> scores[:, eos] = -inf while
+                   cur_len <= min_length (risk U4 [MEMORY]: one step longer than the PyTorch processor)
     FlaxForcedBOS: at cur_len == 1 -> all -inf except forced id = 0
     FlaxForcedEOS: at cur_len == max_length - 1 -> all -inf except forced id = 0"""
     s = scores
     if min_length is not None and eos_token_id is not None and min_length > -1:
-        if cur_len < min_length:
+        if 1 - int(np.clip(cur_len - min_length, 0, 1)):
             s = s.copy()
             s[:, eos_token_id] = -np.inf
     if forced_bos_token_id is not None and cur_len == 1:

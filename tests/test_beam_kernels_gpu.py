@@ -59,7 +59,7 @@ def cuda_beam_search(logits_fn, B, K, L, *, eos=2, pad=1, start=2, forced_bos=No
         if forced < 0:
             seqs = st["running_seq"].reshape(R, L).cpu().numpy()
             lp = rg.log_softmax(logits_fn(cur_len, seqs))
-            if min_length is not None and min_length > -1 and cur_len < min_length:
+            if min_length is not None and min_length > -1 and cur_len <= min_length:
                 lp[:, eos] = -np.inf
             val, idx = rg.top_k(lp, cpr)
             ws["row_lp"].copy_(torch.from_numpy(val))

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(l, name), f"{name} declared in include/mic_b200.h but not exported"
     # and the Python binding table covers exactly the header
     assert sorted(_lib.EXPORTED) == declared
-    assert l.mic_abi_version() == 1
+    assert l.mic_abi_version() == 2
 
 
 def test_sass_contains_blackwell_tensor_and_tma_ops():

@@ -241,8 +241,7 @@ def test_adamw_matches_oracle():
     for count in range(3):
         lr = rm.linear_warmup_decay_lr(count + 5, 5e-3, 10, 100)
         t = count + 1
-        hp = torch.tensor([lr, 0.9, 0.999, 1e-8, 0.01, 1 / (1 - 0.9 ** t), 1 / (1 - 0.999 ** t), 1.0], device=DEV)
-        ops.adamw(p, m, v, g, shadow, hp)
+        ops.adamw(p, m, v, g, shadow, lr, 0.9, 0.999, 1e-8, 0.01, 1 / (1 - 0.9 ** t), 1 / (1 - 0.999 ** t), 1.0)
         pn, mn, vn = rm.adamw_update(pn, g.cpu().numpy(), mn, vn, count, lr, weight_decay=0.01)
     torch.cuda.synchronize()
     np.testing.assert_allclose(p.cpu().numpy(), pn, rtol=2e-5, atol=2e-6)

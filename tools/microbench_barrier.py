@@ -6,11 +6,12 @@ import mic_b200
 from mic_b200 import _lib
 
 lib = _lib.lib()
-sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+sync = torch.zeros(256, dtype=torch.int32, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
-names = {0: "as used", 1: "poll without sleep", 2: "+ __threadfence per thread", 3: "256 pollers per CTA"}
-for variant in (0, 1, 2, 3):
-    for n in (1, 1001):
+names = {0: "counter (atom.add.release)", 1: "poll without sleep", 2: "+ __threadfence per thread", 3: "256 pollers per CTA",
+         4: "per-CTA flag words, warp polls"}
+for variant in (0, 1, 2, 3, 4):
+    for n in (2, 1002):
         for _ in range(3):
             lib.mic_barrier_bench(s, sync.data_ptr(), n, variant)
         torch.cuda.synchronize()
@@ -20,8 +21,8 @@ for variant in (0, 1, 2, 3):
             lib.mic_barrier_bench(s, sync.data_ptr(), n, variant)
         e1.record(); torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 10 * 1e3
-        if n == 1:
+        if n == 2:
             base = t
         else:
-            print(f"variant {variant} ({names[variant]:28s}): {(t - base) / 1000:.3f} us per barrier (kernel with 1 barrier: {base:.1f} us)")
-assert int(sync.item()) == 0
+            print(f"variant {variant} ({names[variant]:28s}): {(t - base) / 1000:.3f} us per barrier (kernel with 2 barriers: {base:.1f} us)")
+assert int(sync[0].item()) == 0

@@ -25,9 +25,17 @@ G = torch.cuda.get_device_properties(0).multi_processor_count
 P = 1 + 11 * L
 prof = torch.zeros(P * G + 256, dtype=torch.int64, device="cuda")
 pos = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+opts = int(sys.argv[3]) if len(sys.argv) > 3 else ops.DECODER_STEP_OPTS[0]
 for _ in range(3):
-    ops.decoder_step(plan, L, R, pos, sync, prof)
+    ops.decoder_step(plan, L, R, pos, sync, prof, opts=opts)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    ops.decoder_step(plan, L, R, pos, sync, None, opts=opts)
+e1.record()
+torch.cuda.synchronize()
+print(f"opts={opts}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch (20 back-to-back launches, CUDA events)")
 raw = prof.cpu().numpy().astype(np.int64)
 t = raw[:P * G].reshape(P, G)
 tr = raw[P * G:]
