@@ -142,6 +142,11 @@ int mic_batch_sum(void* stream, const void* x, int B, int T, int d, float* out, 
  * order; trunc_int reproduces the int32 cast of encode() modeling_clip_vision_mbart.py:330. */
 int mic_patchify(void* stream, const float* pixels, void* out, int B, int image_size, int patch, int channel_first,
                  int trunc_int);
+/* Input hand-off [SURVEY 8f-2]: uint8 pixels as the data pipeline holds them after Resize/CenterCrop
+ * (main.py:171-172); ConvertImageDtype(float) = x/255 and Normalize(mean, std) (main.py:173-174) are applied here,
+ * fused with the patch gather.  mean3 / std3: HOST pointers to 3 floats (copied into the launch). */
+int mic_patchify_u8(void* stream, const unsigned char* pixels, void* out, int B, int image_size, int patch,
+                    int channel_first, int trunc_int, const float* mean3, const float* std3);
 int mic_vit_embed_ln_fwd(void* stream, const void* patch_out, const float* patch_bias, const void* cls,
                          const void* pos, const float* gamma, const float* beta, float eps, int use_ln, void* emb,
                          void* y, float* mean, float* rstd, int B, int S, int d);
@@ -238,8 +243,8 @@ int mic_decoder_plan_init(void* stream, void* plan_dev, const mic_decoder_layer_
  * CTA's arrival at the end of each phase (profiling aid: tools/profile_decoder_step.py).
  * active (optional): device flag of the search loop's while_loop condition (generation_clip_vision_utils.py:798-820,
  * written by mic_beam_cond / mic_greedy_cond); 0 = the loop has ended and the step is skipped.
- * opts: bit 0 = no writer-side generic->async proxy fences, bit 1 = per-CTA flag barrier instead of the counter
- * (tuning switches; results identical). */
+ * opts: bit 0 = additionally fence generic->async on the writer side of every phase (diagnostic; the readers'
+ * fence after their acquire is what orders the proxies; results identical). */
 int mic_decoder_step(void* stream, const void* plan_dev, int num_layers, int R, int pos, unsigned int* sync_counter,
                      unsigned long long* phase_times, const int* active, int opts);
 

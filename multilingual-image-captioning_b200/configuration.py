@@ -28,6 +28,9 @@ class CLIPVisionConfig:
     pre_layernorm: bool = True      # CLIP `pre_layrnorm`
     final_layernorm: bool = False   # ViT `layernorm` applied to last_hidden_state
     channel_first_input: bool = False  # modeling_vit_bart.py:445 transposes NCHW -> NHWC
+    # Normalize(mean, std) of the reference's Transform (main.py:174); applied in-kernel when uint8 pixels are handed in
+    image_mean: tuple = (0.48145466, 0.4578275, 0.40821073)
+    image_std: tuple = (0.26862954, 0.26130258, 0.27577711)
 
     @property
     def num_patches(self) -> int:

@@ -764,26 +764,31 @@ __device__ __forceinline__ void decode_self_attn_runs(const DecAttnArgs& a, int 
     attn_issue_runs(hb, rowpitch, nk, row0, row1, kv_smem, bar_k, lane);
     attn_issue_runs(hb + plane, rowpitch, nk, row0, row1, kv_smem + 8192, bar_v, lane);
   }
+  // query stage: row 0 = the item's query (pre-scaled: 1/8 is exact), rows 1..7 stay zero for every item of the phase.
+  // Lanes 0..7 own the 8 chunks of row 0; the NEXT item's query is loaded one item ahead (its L2 round trip runs
+  // under this item's S = Q K^T instead of in front of the next one).
+  float qn[8];
+  {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int id = lane + t * 32;
+      if (id >= 8) *reinterpret_cast<uint4*>(q_stage + (id >> 3) * QP + (id & 7) * 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (lane < 8) load8_cg(a.q + (long long)(i / a.H) * a.ldq + (i % a.H) * HD + lane * 8, qn);
+  }
   while (true) {
     const int r = i / a.H, h = i % a.H;
     const int inext = i + stride;
     const bool has_next = inext < items;
     int nrow0 = 0, nrow1 = 0;
-    if (has_next) decode_attn_rows(a, inext / a.H, lane, &nrow0, &nrow1);
-    // query row -> bf16 stage row 0 (pre-scaled: 1/8 is exact), rows 1..7 zero: 64 chunks, 2 per lane
+    if (lane < 8) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int id = lane + t * 32;
-      const int rr = id >> 3, c8 = (id & 7) * 8;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
-      if (rr == 0) {
-        load8_cg(a.q + (long long)r * a.ldq + h * HD + c8, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] *= a.scale;
-      }
-      store8(q_stage + rr * QP + c8, f);
+      for (int j = 0; j < 8; ++j) qn[j] *= a.scale;
+      store8(q_stage + lane * 8, qn);
+    }
+    if (has_next) {
+      decode_attn_rows(a, inext / a.H, lane, &nrow0, &nrow1);
+      if (lane < 8) load8_cg(a.q + (long long)(inext / a.H) * a.ldq + (inext % a.H) * HD + lane * 8, qn);
     }
     __syncwarp();
     mbar_wait(bar_k, *par_k);

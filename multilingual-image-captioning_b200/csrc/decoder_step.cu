@@ -45,9 +45,12 @@ constexpr int BAR_BYTES = 512;               // 2*STAGES + 4 + 2*EW mbarriers + 
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + VEC_SCRATCH + BAR_BYTES + 1024;
 
 enum { PH_GEMM_STORE = 0, PH_GEMM_RED = 1, PH_LN = 2, PH_ATTN = 3 };
-// barrier state (256 uint32, zero before the first launch): [0] arrival counter of the counter barrier,
-// [SYNC_EPOCH] launch-epoch base of the flag barrier, [SYNC_FLAGS + cta] phases completed by each CTA (+ epoch base)
-constexpr int SYNC_EPOCH = 32, SYNC_FLAGS = 64, OPT_NO_WRITER_FENCE = 1, OPT_FLAG_BARRIER = 2;
+// barrier state (256 uint32, zero before the first launch): [0] = arrival counter.  A per-CTA flag-word barrier
+// ([SYNC_FLAGS + cta] = phases completed, launch epoch in [SYNC_EPOCH]; st.release arrival, one polling warp per CTA) was
+// built and measured in round 2: 1.49 us bare vs 1.35 us for the counter, and 1,389 vs 1,015 us for the whole step
+// (148 polling warps x 5 words load the L2 far more than 148 single-word pollers) -> only the microbenchmark keeps it
+// (barrier_bench_kernel variant 4, profiles/r02_barrier_microbench.txt).
+constexpr int SYNC_EPOCH = 32, SYNC_FLAGS = 64, OPT_KEEP_WRITER_FENCE = 1;
 
 struct Phase {
   int kind;
@@ -87,7 +90,8 @@ struct StepArgs {
   unsigned long long* prof;       // optional [num_phases, gridDim] globaltimer stamps of each CTA's phase arrival
   const int* active;              // optional device flag of the search loop (beam_cond / greedy_cond): 0 = every
                                   // hypothesis finished -> the whole step is skipped (the while_loop has ended)
-  int opts;                       // bit 0: no writer-side generic->async proxy fence (readers fence after their acquire)
+  int opts;                       // bit 0: ALSO fence generic->async on the writer side (readers always fence after their
+                                  // acquire, which is what orders the proxies; the extra fence cost 45 us per step)
 };
 
 // ---- The role loops below are written for INSTRUCTION COUNT: each is a single thread (or a single warp per work
@@ -146,9 +150,6 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
   const int P = args.num_phases;
   const Phase* phases = args.phases;
   const int m_tiles = (args.R + BM - 1) / BM;
-  const bool flag_bar = (args.opts & OPT_FLAG_BARRIER) != 0;
-  const unsigned int* flags = args.sync + SYNC_FLAGS;
-  const unsigned int epoch = flag_bar ? ld_relaxed_gpu(args.sync + SYNC_EPOCH) : 0u;   // set by the previous launch
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -198,7 +199,6 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
     }
   } else if (warp == 3) {
     // ===================== activation producer: gated on the grid barrier of the previous phase ==========
-    // (lane 0 issues the copies; with the flag barrier the whole warp polls the per-CTA flags)
     int slot = 0, round = 0;
     for (int p = 0; p < P; ++p) {
       const Phase& ph = phases[p];
@@ -207,13 +207,11 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       if (cta >= units) continue;
       Unit t = unit_of(ph, cta, m_tiles);              // address arithmetic of the first unit before the wait
       if (p > 0) {
-        if (flag_bar) {
-          flags_wait_warp(flags, G, epoch + (unsigned int)p, lane);
-        } else if (lane == 0) {
+        if (lane == 0) {
           while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
           fence_acquire_gpu();
+          fence_proxy_async_global();
         }
-        if (lane == 0) fence_proxy_async_global();
       }
       if (lane == 0) {
         const bool trc = args.prof && cta == TRACE_CTA && p == TRACE_PHASE;
@@ -301,8 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
         if (cta >= units && p > 0) {
           // no work here: still do not arrive for phase p before phase p-1 is complete everywhere, so that
           // (arrivals / G) counts whole phases (CTAs with work inherit this from their gated activation loads)
-          // (flag barrier: a CTA's word counts ITS completed phases, so an idle CTA may run ahead)
-          if (leader && !flag_bar) {
+          if (leader) {
             while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
             fence_acquire_gpu();
           }
@@ -370,9 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       } else {
         // vector phase: inputs come from earlier phases of other CTAs
         if (p > 0) {
-          if (flag_bar) {
-            if (ew == 0) flags_wait_warp(flags, G, epoch + (unsigned int)p, lane);
-          } else if (leader) {
+          if (leader) {
             while ((int)(ld_relaxed_gpu(args.sync) / (unsigned int)G) < p) __nanosleep(20);
             fence_acquire_gpu();
           }
@@ -466,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 130] = gtime();
       // only phases whose output is fetched by bulk copies (tile-image activations) or that used the ring as scratch
       // need the generic -> async proxy fence (0.6 us); split-K reductions and the q|k|v store feed generic loads
-      if (!(args.opts & 1) &&
+      if ((args.opts & OPT_KEEP_WRITER_FENCE) &&
           (ph.kind == PH_LN || ph.kind == PH_ATTN || (ph.kind == PH_GEMM_STORE && (ph.out_tiled_kb || ph.out2))))
         fence_proxy_async_global();
       if (args.prof && cta == TRACE_CTA && p == TRACE_PHASE && leader) args.prof[(long long)P * G + 131] = gtime();
@@ -475,16 +470,10 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_step_kernel(const StepArgs
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (leader) {
         if (args.prof) args.prof[(long long)p * G + cta] = gtime();
-        if (flag_bar) {
-          st_release_gpu(args.sync + SYNC_FLAGS + cta, epoch + (unsigned int)p + 1u);
-          // CTA 0 got here only after every CTA completed phase P-2, i.e. long after all of them read the epoch
-          if (p == P - 1 && cta == 0) *reinterpret_cast<volatile unsigned int*>(args.sync + SYNC_EPOCH) = epoch + (unsigned int)P;
-        } else {
-          const unsigned int old = atom_add_release_gpu(args.sync, 1u);
-          if (p == P - 1 && old == (unsigned int)P * (unsigned int)G - 1u) {
-            __threadfence();
-            *reinterpret_cast<volatile unsigned int*>(args.sync) = 0u;     // last arrival of the launch: re-arm
-          }
+        const unsigned int old = atom_add_release_gpu(args.sync, 1u);
+        if (p == P - 1 && old == (unsigned int)P * (unsigned int)G - 1u) {
+          __threadfence();
+          *reinterpret_cast<volatile unsigned int*>(args.sync) = 0u;     // last arrival of the launch: re-arm
         }
       }
     }

@@ -475,6 +475,34 @@ patchify_kernel(const float* __restrict__ px, bf16* __restrict__ out, int B, int
   }
 }
 
+// Input hand-off: the data pipeline's uint8 image (after Resize / CenterCrop, main.py:171-172) goes
+// straight to the GPU — a quarter of the fp32 bytes over PCIe — and `ConvertImageDtype(torch.float)` (x / 255) and
+// `Normalize(mean, std)` (main.py:173-174) happen here, fused with the patch gather and the bf16 conversion.
+struct PixelNorm {
+  float mean[3], inv_std[3];
+};
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ px, bf16* __restrict__ out, int B, int img, int p, int nchw,
+                   int trunc_int, const PixelNorm nrm) {
+  const int g = img / p;
+  const int K = p * p * 3;
+  const long long total = (long long)B * g * g * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long m = i / K;
+    const int c = k % 3, kw = (k / 3) % p, kh = k / (3 * p);
+    const int pw = (int)(m % g), ph = (int)((m / g) % g);
+    const int b = (int)(m / (g * g));
+    const int yy = ph * p + kh, xx = pw * p + kw;
+    const uint8_t u = nchw ? px[(((long long)b * 3 + c) * img + yy) * img + xx]
+                           : px[(((long long)b * img + yy) * img + xx) * 3 + c];
+    // torchvision: convert_image_dtype = x / 255 (fp32 division), normalize = (x - mean) / std (fp32 division)
+    float v = (__fdiv_rn((float)u, 255.0f) - nrm.mean[c]) * nrm.inv_std[c];
+    if (trunc_int) v = truncf(v);
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // tokens: [cls ; patch_out(+bias)] + pos -> emb (bf16) -> optional LayerNorm -> y.  One warp per token row.
 __global__ void __launch_bounds__(256)
 vit_embed_ln_fwd_kernel(const bf16* __restrict__ patch_out, const float* __restrict__ patch_bias,
@@ -831,6 +859,23 @@ extern "C" int mic_patchify(void* stream, const float* pixels, void* out, int B,
   const long long total = (long long)B * image_size * image_size * 3;
   patchify_kernel<<<grid_for(total, 256 * 4), 256, 0, STREAM>>>(pixels, (bf16*)out, B, image_size, patch,
                                                                 channel_first, trunc_int);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
+
+extern "C" int mic_patchify_u8(void* stream, const unsigned char* pixels, void* out, int B, int image_size, int patch,
+                               int channel_first, int trunc_int, const float* mean3, const float* std3) {
+  MIC_CHECK_ARG(image_size % patch == 0, "image size %d not divisible by patch %d", image_size, patch);
+  MIC_CHECK_ARG(pixels && out && mean3 && std3, "patchify_u8: null argument");
+  PixelNorm nrm;
+  for (int c = 0; c < 3; ++c) {
+    MIC_CHECK_ARG(std3[c] > 0.f, "patchify_u8: std[%d] must be positive", c);
+    nrm.mean[c] = mean3[c];
+    nrm.inv_std[c] = 1.0f / std3[c];
+  }
+  const long long total = (long long)B * image_size * image_size * 3;
+  patchify_u8_kernel<<<grid_for(total, 256 * 4), 256, 0, STREAM>>>(pixels, (bf16*)out, B, image_size, patch,
+                                                                   channel_first, trunc_int, nrm);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

@@ -181,9 +181,13 @@ class CaptionEngine:
         B = pixel_values.shape[0]
         S, npatch, dv = c.num_tokens, c.num_patches, c.hidden_size
         Mv = B * S
-        px = pixel_values.to(self.dev, F32).contiguous()
+        # uint8 pixels = the input hand-off (x/255 and Normalize fused into the patch kernel); anything else is the
+        # reference's contract: normalised float pixels (cast to f32, modeling_clip_vision_mbart.py:501)
+        px = pixel_values.to(self.dev).contiguous() if pixel_values.dtype == torch.uint8 else \
+            pixel_values.to(self.dev, F32).contiguous()
         patches = ops.patchify(px, b.get(tag + ".patches", (B * npatch, c.patch_size ** 2 * 3)), B, c.image_size,
-                               c.patch_size, channel_first=c.channel_first_input, trunc_int=trunc_int)
+                               c.patch_size, channel_first=c.channel_first_input, trunc_int=trunc_int,
+                               mean=c.image_mean, std=c.image_std)
         patch_out = ops.gemm(patches, ps.w("v.patch.w"), b_mn=True, out=b.get(tag + ".patch_out", (B * npatch, dv)))
         emb = b.get(tag + ".emb", (Mv, dv))
         st_pre = (b.get(tag + ".pre.mean", (Mv,), F32), b.get(tag + ".pre.rstd", (Mv,), F32))

@@ -246,9 +246,11 @@ def _lm_head_search(engine, cache, hf, mask_token, ws, active=None):
 
 
 def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams, min_length,
-                 forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping):
+                 forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping, trace_cb=None):
     """Enqueue encode + the whole search loop on the current stream (no host synchronisation inside:
-    the while_loop condition lives in the device flag `active`).  Capturable into one CUDA graph."""
+    the while_loop condition lives in the device flag `active`).  Capturable into one CUDA graph.
+    trace_cb(cur_len, ws, st) — eager runs only — is called after the lm_head search of every un-forced step, before
+    the bookkeeping kernel consumes `ws` (parity tests read the candidate lists and the search state there)."""
     t, ps = engine.t, engine.ps
     dev = engine.dev
     B = px.shape[0]
@@ -281,6 +283,8 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
             if forced < 0:
                 mt = eos_token_id if (mask_eos and _min_length_applies(cur_len, min_length)) else -1
                 _lm_head_search(engine, cache, hf, mt, ws, active)
+                if trace_cb is not None:
+                    trace_cb(cur_len, ws, st)
             ops.greedy_step(ws, st, forced, R, Lmax, cur_len, eos_token_id, pad_token_id)
             ops.greedy_cond(st, R, cur_len + 1, Lmax)
         return {"sequences": st["sequences"]}
@@ -301,6 +305,8 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
         if forced < 0:
             mt = eos_token_id if (mask_eos and _min_length_applies(cur_len, min_length)) else -1
             _lm_head_search(engine, cache, hf, mt, ws, active)
+            if trace_cb is not None:
+                trace_cb(cur_len, ws, st)
         ops.beam_step(ws, st, forced, B, K, Lmax, V, cur_len, eos_token_id, early_stopping, length_penalty)
         ops.beam_cond(st, B, K, cur_len + 1, Lmax, length_penalty, early_stopping)
     out_seq = torch.empty((B, Lmax), dtype=I32, device=dev)
@@ -310,7 +316,7 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
 
 
 @torch.no_grad()
-def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_weights=None, **kw):
+def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_weights=None, trace_cb=None, **kw):
     """`generate` :128-336.  encode() truncates pixels to int32 first (modeling_clip_vision_mbart.py:330).
     The first call for a given (batch, search settings) runs eagerly (allocates every buffer); the whole
     loop is then captured into ONE CUDA graph and later calls only copy the pixels in and replay it."""
@@ -320,6 +326,9 @@ def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_w
     # parameters are frozen while the loop runs: GEMMs prefetch weight tiles ahead of their dependency wait
     prefetch_weights = pdl if prefetch_weights is None else prefetch_weights
     ops.launch_options(pdl=int(pdl), gemm_b_static=int(prefetch_weights))
+    if trace_cb is not None:
+        use_cuda_graph = False
+        kw = dict(kw, trace_cb=trace_cb)
     try:
         return _generate(engine, px, use_cuda_graph, (pdl, prefetch_weights), kw)
     finally:

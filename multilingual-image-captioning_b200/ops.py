@@ -29,6 +29,7 @@ def _s():
 
 
 TIMED = {}          # C-ABI name -> list of (start, end) CUDA events recorded around each call (bench.py)
+TIMED_FLOPS = {}    # C-ABI name -> list of 2*M*N*K of the same calls (GEMM family only)
 
 
 def _call(name, *args):
@@ -85,6 +86,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, a
     if act_bwd is not None:          # (activation name, saved pre-activation U): D = (A B^T) o act'(U)
         assert residual is None and bias is None and act_code == 0
         act_code, residual, block_n = -ACT[act_bwd[0]], act_bwd[1], 256
+    if "mic_gemm_bf16" in TIMED:
+        TIMED_FLOPS.setdefault("mic_gemm_bf16", []).append(2.0 * M * N * K)
     _call("mic_gemm_bf16", int(a_mn), int(b_mn), _p(a), _ld(a), _p(b), _ld(b), M, N, K, _p(out), _ld(out),
           int(d_f32), int(accumulate), _p(bias), act_code, _p(pre_act_out), _p(residual),
           _ld(residual) if residual is not None else 0, block_n, group_m, split_k, *_drop(dropout))
@@ -117,6 +120,8 @@ def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws, secon
 def lm_head_ce_stats(h, emb, bias, labels, ws, logits_out=None):
     M, K = h.shape
     V = emb.shape[0]
+    if "mic_lm_head_ce_stats" in TIMED:
+        TIMED_FLOPS.setdefault("mic_lm_head_ce_stats", []).append(2.0 * M * V * K)
     _call("mic_lm_head_ce_stats", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), _p(labels), M, V, K, _p(ws["pmax"]),
           _p(ws["psum"]), _p(ws["psumz"]), _p(ws["zlabel"]), _p(logits_out),
           _ld(logits_out) if logits_out is not None else 0)
@@ -305,8 +310,17 @@ def batch_sum(x, B, T, d, out, out_ld):
     _call("mic_batch_sum", _p(x), B, T, d, _p(out), out_ld)
 
 
-def patchify(pixels, out, B, image_size, patch, channel_first=False, trunc_int=False):
-    assert pixels.dtype == F32 and pixels.is_contiguous()
+def patchify(pixels, out, B, image_size, patch, channel_first=False, trunc_int=False, mean=None, std=None):
+    """fp32 pixels (already normalised, the reference's input contract) or uint8 pixels (input hand-off: x/255 and
+    Normalize(mean, std) of main.py:173-174 are applied in the kernel)."""
+    assert pixels.is_contiguous()
+    if pixels.dtype == torch.uint8:
+        m3 = (ctypes.c_float * 3)(*[float(x) for x in mean])
+        s3 = (ctypes.c_float * 3)(*[float(x) for x in std])
+        _call("mic_patchify_u8", _p(pixels), _p(out), B, image_size, patch, int(channel_first), int(trunc_int),
+              ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p))
+        return out
+    assert pixels.dtype == F32
     _call("mic_patchify", _p(pixels), _p(out), B, image_size, patch, int(channel_first), int(trunc_int))
     return out
 

@@ -137,13 +137,15 @@ def _static_batch(state, batch):
     device-to-device copy into the static inputs."""
     dev = state.store.device
     px = torch.as_tensor(batch["pixel_values"])
-    key = (tuple(px.shape), tuple(torch.as_tensor(batch["decoder_input_ids"]).shape))
+    # uint8 pixels stay uint8 all the way to the patch kernel (input hand-off: a quarter of the H2D bytes)
+    px_dtype = torch.uint8 if px.dtype == torch.uint8 else F32
+    key = (tuple(px.shape), tuple(torch.as_tensor(batch["decoder_input_ids"]).shape), px_dtype)
     sb = state.__dict__.get("_static")
     if sb is None or sb["key"] != key:
         B, T = key[1]
 
         def mk():
-            return {"pixel_values": torch.empty(key[0], dtype=F32, device=dev),
+            return {"pixel_values": torch.empty(key[0], dtype=px_dtype, device=dev),
                     "decoder_input_ids": torch.empty((B, T), dtype=torch.int32, device=dev),
                     "attention_mask": torch.empty((B, T), dtype=torch.int32, device=dev),
                     "input_ids": torch.empty((B, T), dtype=torch.int32, device=dev)}

@@ -252,7 +252,9 @@ def _beam_search(p, enc, config, g, return_trace=False, logits_fn=None, batch_si
         next_running_scores = topk_log_probs[bidx, next_topk_indices]
         if return_trace:
             rest = np.sort(flat, axis=-1)[:, -(2 * K + 1)]
-            trace.append({"cur_len": cur_len, "topk_log_probs": topk_log_probs.copy(), "topk_raw": topk_raw,
+            trace.append({"cur_len": cur_len, "running_sequences": running_sequences.copy(),
+                          "running_scores": running_scores.copy(),
+                          "topk_log_probs": topk_log_probs.copy(), "topk_raw": topk_raw,
                           "did_finish": did_finish.copy(),
                           "topk_indices": topk_indices.copy(), "ninth": rest.copy()})
         # :910-919 (re-uses the penalised topk_log_probs)

@@ -54,6 +54,8 @@ def gen():
         out[f"{name}_beam_ninth"] = np.stack([s["ninth"] for s in tr]).astype(np.float32)             # [steps, B]
         out[f"{name}_beam_did_finish"] = np.stack([s["did_finish"] for s in tr])
         out[f"{name}_beam_topk_indices"] = np.stack([s["topk_indices"] for s in tr]).astype(np.int64)
+        out[f"{name}_beam_running_seq"] = np.stack([s["running_sequences"] for s in tr]).astype(np.int32)   # at step entry
+        out[f"{name}_beam_running_scores"] = np.stack([s["running_scores"] for s in tr]).astype(np.float32)
         print(name, "beam", time.time() - t0, "s; steps", len(tr), r["sequences"][:2, :12], r["scores"], flush=True)
         del params
     np.savez_compressed(os.path.join(HERE, "config3_full_gen_golden.npz"), **out)
