@@ -88,11 +88,14 @@ int mic_lm_head_search_num_partials(int M);
  * after the row's pair are considered (pass the 8th best of the first pass, mic_search_merge last_val/last_idx);
  * the partial statistics of such a pass are meaningless.
  * active (optional): device flag of the search loop's while_loop condition (generation_clip_vision_utils.py:798-820);
- * 0 = the loop has ended, the kernel returns without touching its outputs. */
+ * 0 = the loop has ended, the kernel returns without touching its outputs.
+ * gumbel_key (optional, HOST pointer to 2 uint32): `_sample` generation_clip_vision_utils.py:537-663 — Gumbel noise
+ * of jax.random.categorical's threefry2x32 stream for this key is added to every logit, so candidate 0 of a row is
+ * the sampled token (the log-softmax partials are meaningless then). */
 int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
                        const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
                        float* cand_val, int* cand_idx, const float* upper_val, const int* upper_idx,
-                       const int* active);
+                       const int* active, const unsigned int* gumbel_key);
 
 /* packed-operand variant of mic_lm_head_search: H and E are given as K-major tile images (mic_pack_kmajor_tiles:
  * H with tile_rows = 128 - the persistent decoder step writes it directly -, E with tile_rows = 256), so that a
@@ -102,7 +105,8 @@ long long mic_pack_kmajor_tiles_bytes(long long rows, int K, int tile_rows);
 int mic_pack_kmajor_tiles(void* stream, const void* src, long long ld, long long rows, int K, int tile_rows, void* out);
 int mic_lm_head_search_packed(void* stream, const void* h_tiles, const void* e_tiles, const float* bias,
                               int mask_token, int M, int V, int K, float* pmax, float* psum, float* cand_val,
-                              int* cand_idx, const float* upper_val, const int* upper_idx, const int* active);
+                              int* cand_idx, const float* upper_val, const int* upper_idx, const int* active,
+                              const unsigned int* gumbel_key);
 
 /* ---- normalisation / embedding / elementwise (HBM-bound, vectorised, warp-shuffle reductions) ----
  * flax.linen.LayerNorm (fp32 statistics, var = E[x^2]-E[x]^2) as used by FlaxCLIPEncoderLayer,

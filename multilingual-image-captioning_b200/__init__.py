@@ -13,10 +13,13 @@ from . import synthetic
 _LAZY = {
     "FlaxCLIPVisionMBartForConditionalGeneration": ".modeling_clip_vision_mbart",
     "Seq2SeqLMOutput": ".modeling_clip_vision_mbart",
+    "FlaxViTBartForConditionalGeneration": ".modeling_vit_bart",
     "TrainState": ".training", "train_step": ".training", "eval_step": ".training",
-    "create_learning_rate_fn": ".training",
+    "create_learning_rate_fn": ".training", "adamw": ".training", "AdamWConfig": ".training",
+    "save_model_checkpoint": ".training", "restore_model_checkpoint": ".training", "rotate_checkpoints": ".training",
 }
-_LAZY_MODULES = ("ops", "engine", "generation", "training", "params", "modeling_clip_vision_mbart", "_lib")
+_LAZY_MODULES = ("ops", "engine", "generation", "training", "params", "modeling_clip_vision_mbart", "modeling_vit_bart",
+                 "checkpoint", "_lib")
 
 
 def __getattr__(name):

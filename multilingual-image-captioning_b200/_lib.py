@@ -42,10 +42,10 @@ SIGNATURES = {
     "mic_ce_finalize": [P, P, P, P, P, P, I, I, I, F, P, P, P, P],
     "mic_lm_head_ce_grad": [P, P, L, P, L, P, P, P, P, F, F, I, I, I, P, L],
     "mic_lm_head_search_num_partials": [I],
-    "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P, P, P, P],
+    "mic_lm_head_search": [P, P, L, P, L, P, I, I, I, I, P, P, P, P, P, P, P, P],
     "mic_pack_kmajor_tiles_bytes": [L, I, I],
     "mic_pack_kmajor_tiles": [P, P, L, L, I, I, P],
-    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
+    "mic_lm_head_search_packed": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, P],
     "mic_layernorm_fwd": [P, P, P, P, F, P, P, P, I, I],
     "mic_residual_ln_fwd": [P, P, P, P, P, P, F, P, I, I],
     "mic_layernorm_bwd_workspace_floats": [I, I],

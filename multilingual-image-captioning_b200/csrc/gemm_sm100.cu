@@ -307,13 +307,14 @@ extern "C" int mic_lm_head_search_num_partials(int M) { return 2 * (search_grid(
 extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
                                   const float* bias, int mask_token, int M, int V, int K, float* pmax, float* psum,
                                   float* cand_val, int* cand_idx, const float* upper_val, const int* upper_idx,
-                                  const int* active) {
+                                  const int* active, const unsigned int* gumbel_key) {
   const int mb = (M + BLOCK_M - 1) / BLOCK_M;
   MIC_CHECK_ARG(mb <= mic_num_sms(), "lm_head_search: M=%d rows exceed one m-block per SM", M);
   Operands o;
   int rc = setup_operands(&o, 0, 0, H, ldh, E, lde, M, V, K, 256, mb);
   if (rc) return rc;
-  EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, nullptr, nullptr, upper_val, upper_idx, active};
+  EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, nullptr, nullptr, upper_val, upper_idx, active,
+                        gumbel_key != nullptr, gumbel_key ? gumbel_key[0] : 0u, gumbel_key ? gumbel_key[1] : 0u};
   // fixed m-block per CTA: grid is a multiple of num_m_blocks and tiles are rasterised m-fastest
   auto kern = gemm_kernel<0, 0, 256, EpiSearch>;
   static bool attr_set = false;
@@ -368,7 +369,7 @@ extern "C" int mic_pack_kmajor_tiles(void* stream, const void* src, long long ld
 extern "C" int mic_lm_head_search_packed(void* stream, const void* h_tiles, const void* e_tiles, const float* bias,
                                          int mask_token, int M, int V, int K, float* pmax, float* psum,
                                          float* cand_val, int* cand_idx, const float* upper_val,
-                                         const int* upper_idx, const int* active) {
+                                         const int* upper_idx, const int* active, const unsigned int* gumbel_key) {
   const int mb = (M + BLOCK_M - 1) / BLOCK_M;
   MIC_CHECK_ARG(mb <= mic_num_sms(), "lm_head_search: M=%d rows exceed one m-block per SM", M);
   MIC_CHECK_ARG(K % 64 == 0 && h_tiles && e_tiles, "lm_head_search_packed: K=%d must be a multiple of 64", K);
@@ -387,7 +388,8 @@ extern "C" int mic_lm_head_search_packed(void* stream, const void* h_tiles, cons
   s.split_k = 1;
   s.kb_per_split = K / BLOCK_K;
   EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, (const bf16*)h_tiles, (const bf16*)e_tiles,
-                        upper_val, upper_idx, active};
+                        upper_val, upper_idx, active,
+                        gumbel_key != nullptr, gumbel_key ? gumbel_key[0] : 0u, gumbel_key ? gumbel_key[1] : 0u};
   auto kern = gemm_kernel<0, 0, 256, EpiSearchPacked>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -501,7 +501,53 @@ struct EpiSearchParams {
   // device flag of the search loop's while_loop condition (null = always run): 0 -> the kernel returns at once, the
   // (stale) partial lists are ignored by the equally gated bookkeeping kernels
   const int* active;
+  // `_sample` (generation_clip_vision_utils.py:537-663): next = jax.random.categorical(key, raw logits) =
+  // argmax(logits + Gumbel noise).  gumbel_on: every value gets -log(-log(u)) with u from the threefry2x32 stream of
+  // (gumbel_k0, gumbel_k1) at the element's flat index in the [M, N] logits array, so the row's top-1 IS the sample.
+  int gumbel_on;
+  unsigned int gumbel_k0, gumbel_k1;
 };
+
+// jax._src.random (0.2.16, pinned by requirements.txt:13) restated [MEMORY, see oracle/reference_generate.py]:
+// threefry2x32 with 20 rounds; random_bits(key, 32, shape) evaluates it on counts iota(size) split into halves
+// (x0 = counts[:half], x1 = counts[half:], odd sizes padded with one 0), output = concat(y0, y1);
+// uniform(minval = tiny, maxval = 1): f = bitcast((bits >> 9) | 0x3f800000) - 1, u = max(tiny, f * (1 - tiny) + tiny);
+// gumbel = -log(-log(u)).
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      x0 += x1;
+      x1 = rotl32(x1, R[g & 1][r]);
+      x1 ^= x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+  }
+}
+__device__ __forceinline__ float gumbel_at(uint32_t k0, uint32_t k1, unsigned long long i, unsigned long long total) {
+  const unsigned long long half = (total + 1) >> 1;
+  uint32_t x0, x1;
+  if (i < half) {
+    x0 = (uint32_t)i;
+    x1 = (i + half < total) ? (uint32_t)(i + half) : 0u;      // the pad element of an odd-sized count array
+  } else {
+    x0 = (uint32_t)(i - half);
+    x1 = (uint32_t)i;
+  }
+  threefry2x32(k0, k1, x0, x1);
+  const uint32_t bits = (i < half) ? x0 : x1;
+  const float f = __uint_as_float((bits >> 9) | 0x3f800000u) - 1.0f;
+  const float tiny = 1.17549435e-38f;
+  const float u = fmaxf(tiny, f * (1.0f - tiny) + tiny);
+  return -logf(-logf(u));
+}
 
 // The launcher sizes the grid as a multiple of num_m_blocks with group_m == num_m_blocks, so every CTA
 // keeps the SAME m-block for all of its tiles: the running (max, sum) and the running top-8 of a row live
@@ -561,6 +607,15 @@ struct EpiSearch {
 #pragma unroll
       for (int j = 0; j < 64; ++j)
         if (!(v[j] < st.uv || (v[j] == st.uv && col0 + j > st.ui))) v[j] = -INFINITY;
+    }
+    if (p.gumbel_on) {
+      const unsigned long long total = (unsigned long long)s.M * (unsigned long long)s.N;
+      const unsigned long long base = (unsigned long long)ctx.row * (unsigned long long)s.N + (unsigned long long)col0;
+      if (ctx.row < s.M) {
+#pragma unroll 4
+        for (int j = 0; j < 64; ++j)
+          if (col0 + j < s.N) v[j] += gumbel_at(p.gumbel_k0, p.gumbel_k1, base + j, total);
+      }
     }
     float cmax = v[0];
 #pragma unroll

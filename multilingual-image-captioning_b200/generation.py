@@ -43,9 +43,13 @@ def decode_step(engine, cache: DecodeCache, tokens, pos: int):
     Weight-streaming regime (R = batch*beams rows): every GEMM uses 64-wide tiles so a weight matrix is
     pulled by many SMs at once; the three residual GEMMs of a layer (self out_proj, cross out_proj, fc2)
     additionally split K and reduce-add into one fp32 accumulator, which the next LayerNorm kernel folds
-    into the residual stream (x += acc + bias; y = LN(x); acc = 0) - no bias/residual epilogue, no memset."""
+    into the residual stream (x += acc + bias; y = LN(x); acc = 0) - no bias/residual epilogue, no memset.
+
+    pre-LN (mBART):  x is the residual stream, `a` = LN(x) feeds each sub-block.
+    post-LN (BART, the flax_vit_bart variant): h = LN(h + sublayer(h)) — the SAME fused kernel applied to
+    (cur, other): other = LN(cur + acc + bias); the normalised `other` then IS the residual stream, so the two
+    buffers swap roles after every sub-block; BART has no final layer_norm."""
     t, ps, b = engine.t, engine.ps, engine.bufs
-    assert t.pre_layernorm, "cached decode is implemented for the pre-LN (mBART) decoder"
     R, d, H, T = cache.rows, t.d_model, t.decoder_attention_heads, cache.T
     S = engine.c.num_tokens
     L = t.decoder_layers
@@ -60,34 +64,53 @@ def decode_step(engine, cache: DecodeCache, tokens, pos: int):
     sk_d = max(1, min(4, d // 256))
     sk_f = max(1, min(8, t.decoder_ffn_dim // 512))
     L2 = L * 2 * d
+    pre = t.pre_layernorm
     # embedding (+ positions) -> x ; every row sits at the same position: pos_mod=1 -> 0 + (pos + offset)
     ops.embed_ln_fwd(tokens, None, 1, pos + t.position_offset, ps.w("shared"), ps.w("d.pos"), engine.emb_scale,
                      ps.f("d.ln_emb.scale"), ps.f("d.ln_emb.bias"), eps, None, x)
-    engine._ln_fwd(x, "d.0.ln_sa", eps, a)
+    if pre:
+        engine._ln_fwd(x, "d.0.ln_sa", eps, a)
+        inp = a
+    else:
+        inp = x                                                      # post-LN: sub-blocks read the stream itself
+    cur, other = x, a
     for l in range(L):
         n = f"d.{l}"
+
+        def close(bias_name, ln_name):
+            """Fold the sub-block's output (acc + bias) into the stream and normalise.  Returns the next input."""
+            nonlocal cur, other
+            ops.residual_ln_fwd(acc, ps.f(bias_name), cur, ps.f(ln_name + ".scale"), ps.f(ln_name + ".bias"), eps, other)
+            if pre:
+                return other                                         # cur stays the stream, other = LN(cur)
+            cur, other = other, cur                                  # post-LN: the normalised tensor is the stream
+            return cur
         wqkv, bqkv = ps.w(n + ".sa_qkv.w"), ps.f(n + ".sa_qkv.b")
-        ops.gemm(a, wqkv[:, :d], b_mn=True, bias=bqkv[:d], out=q)
+        ops.gemm(inp, wqkv[:, :d], b_mn=True, bias=bqkv[:d], out=q)
         kv_slot = cache.self_kv[l, :, pos, :]                      # [R, 2d] view, row pitch T*2d: written in place
-        ops.gemm(a, wqkv[:, d:], b_mn=True, bias=bqkv[d:], out=kv_slot)
+        ops.gemm(inp, wqkv[:, d:], b_mn=True, bias=bqkv[d:], out=kv_slot)
         kc = cache.self_kv[l].view(R * T, 2 * d)
         ops.decode_attention(q, kc[:, :d], kc[:, d:], 2 * d, cache.ancestors, T, pos + 1, 1, o, R, H, scale)
         ops.gemm(o, ps.w(n + ".sa_o.w"), b_mn=True, out=acc, accumulate=True, split_k=sk_d, block_n=64)
-        ops.residual_ln_fwd(acc, ps.f(n + ".sa_o.b"), x, ps.f(n + ".ln_ca.scale"), ps.f(n + ".ln_ca.bias"), eps, a)
-        ops.gemm(a, ps.w(n + ".ca_q.w"), b_mn=True, bias=ps.f(n + ".ca_q.b"), out=q)
+        inp = close(n + ".sa_o.b", n + (".ln_ca" if pre else ".ln_sa"))
+        ops.gemm(inp, ps.w(n + ".ca_q.w"), b_mn=True, bias=ps.f(n + ".ca_q.b"), out=q)
         ek = cache.enc_kv[:, l * 2 * d: l * 2 * d + d]
         ev = cache.enc_kv[:, l * 2 * d + d: (l + 1) * 2 * d]
         ops.decode_attention(q, ek, ev, L2, None, S, S, cache.rows_per_image, o, R, H, scale)
         ops.gemm(o, ps.w(n + ".ca_o.w"), b_mn=True, out=acc, accumulate=True, split_k=sk_d, block_n=64)
-        ops.residual_ln_fwd(acc, ps.f(n + ".ca_o.b"), x, ps.f(n + ".ln_f.scale"), ps.f(n + ".ln_f.bias"), eps, a)
-        ops.gemm(a, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=t.activation_function, out=g)
+        inp = close(n + ".ca_o.b", n + (".ln_f" if pre else ".ln_ca"))
+        ops.gemm(inp, ps.w(n + ".fc1.w"), b_mn=True, bias=ps.f(n + ".fc1.b"), act=t.activation_function, out=g)
         ops.gemm(g, ps.w(n + ".fc2.w"), b_mn=True, out=acc, accumulate=True, split_k=sk_f, block_n=64)
-        nxt = f"d.{l + 1}.ln_sa" if l + 1 < L else ("d.ln_final" if t.final_layer_norm else None)
-        if nxt is not None:
-            ops.residual_ln_fwd(acc, ps.f(n + ".fc2.b"), x, ps.f(nxt + ".scale"), ps.f(nxt + ".bias"), eps, a)
-        else:   # no final LayerNorm (BART): fold the residual with an identity-free pass through LN of nothing
-            raise NotImplementedError("decoder without a final LayerNorm is not wired for cached decode")
-    return a
+        if pre:
+            nxt = f"d.{l + 1}.ln_sa" if l + 1 < L else ("d.ln_final" if t.final_layer_norm else None)
+            if nxt is None:
+                raise NotImplementedError("pre-LN decoder without a final LayerNorm is not wired for cached decode")
+            inp = close(n + ".fc2.b", nxt)
+        else:
+            inp = close(n + ".fc2.b", n + ".ln_f")
+    if not pre and t.final_layer_norm:
+        raise NotImplementedError("post-LN decoder with a final LayerNorm is not wired for cached decode")
+    return inp
 
 
 def fused_cache_rowmajor(engine, cache: DecodeCache):
@@ -205,6 +228,43 @@ def _search_ws(engine, R, cand_per_row=8):
             "last_val": b.get("gen.last_val", (R,), F32), "last_idx": b.get("gen.last_idx", (R,), I32)}
 
 
+# ---- jax.random key handling for `_sample` (host side; the per-element stream is generated in the search kernel) ----
+def _threefry2x32_host(k0, k1, x0, x1):
+    """threefry2x32, 20 rounds, on Python ints (jax._src.random at the pinned jax==0.2.16, [MEMORY] risk U9)."""
+    m = 0xFFFFFFFF
+    ks = (k0 & m, k1 & m, (k0 ^ k1 ^ 0x1BD11BDA) & m)
+    rot = ((13, 15, 26, 6), (17, 29, 16, 24))
+    x0, x1 = (x0 + ks[0]) & m, (x1 + ks[1]) & m
+    for g in range(5):
+        for r in rot[g & 1]:
+            x0 = (x0 + x1) & m
+            x1 = ((x1 << r) | (x1 >> (32 - r))) & m
+            x1 ^= x0
+        x0 = (x0 + ks[(g + 1) % 3]) & m
+        x1 = (x1 + ks[(g + 2) % 3] + g + 1) & m
+    return x0, x1
+
+
+def prng_key_pair(prng_key=None):
+    """A jax PRNG key (uint32[2]) / int seed / None (= PRNGKey(0), generation_clip_vision_utils.py:565) -> (k0, k1)."""
+    if prng_key is None:
+        return (0, 0)
+    if isinstance(prng_key, int):
+        return ((prng_key >> 32) & 0xFFFFFFFF, prng_key & 0xFFFFFFFF)
+    if hasattr(prng_key, "detach"):
+        prng_key = prng_key.detach().cpu().numpy()
+    k = [int(x) & 0xFFFFFFFF for x in list(prng_key)]
+    assert len(k) == 2, "a PRNG key is two uint32 words"
+    return (k[0], k[1])
+
+
+def prng_split(key):
+    """jax.random.split(key) -> (first, second): threefry_2x32(key, iota(4)) with counts split into halves."""
+    a0, a1 = _threefry2x32_host(key[0], key[1], 0, 2)
+    b0, b1 = _threefry2x32_host(key[0], key[1], 1, 3)
+    return (a0, b0), (a1, b1)
+
+
 def _min_length_applies(cur_len, min_length):
     """FlaxMinLengthLogitsProcessor (transformers@0085e712 generation_flax_logits_process.py, risk U4 [MEMORY]):
     `apply_penalty = 1 - clip(cur_len - min_length, 0, 1)` — EOS is masked while cur_len <= min_length, one step
@@ -230,7 +290,7 @@ def _step(engine, cache, tokens, pos, active=None):
     return decode_step(engine, cache, tokens, pos)
 
 
-def _lm_head_search(engine, cache, hf, mask_token, ws, active=None):
+def _lm_head_search(engine, cache, hf, mask_token, ws, active=None, gumbel_key=None):
     """lm_head + log-softmax partials + per-row candidates.  8 candidates per row cover 2*num_beams for <= 4 beams;
     5..8 beams run the search a second time restricted to what ranks after the first pass's 8th (exact: both passes
     compute bit-identical logits)."""
@@ -239,14 +299,16 @@ def _lm_head_search(engine, cache, hf, mask_token, ws, active=None):
     for i in range(passes):
         if cache.fused is not None and "e_tiles" in cache.fused:
             ops.lm_head_search_packed(hf, cache.fused["e_tiles"], ps.f("flb"), int(mask_token), cache.rows, t.vocab_size,
-                                      t.d_model, ws, second_pass=i == 1, active=active)
+                                      t.d_model, ws, second_pass=i == 1, active=active, gumbel_key=gumbel_key)
         else:
-            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws, second_pass=i == 1, active=active)
+            ops.lm_head_search(hf, ps.w("shared"), ps.f("flb"), mask_token, ws, second_pass=i == 1, active=active,
+                               gumbel_key=gumbel_key)
         ops.search_merge(ws, cache.rows, second_pass=i == 1)
 
 
 def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams, min_length,
-                 forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping, trace_cb=None):
+                 forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping, trace_cb=None,
+                 sample_key=None):
     """Enqueue encode + the whole search loop on the current stream (no host synchronisation inside:
     the while_loop condition lives in the device flag `active`).  Capturable into one CUDA graph.
     trace_cb(cur_len, ws, st) — eager runs only — is called after the lm_head search of every un-forced step, before
@@ -275,14 +337,20 @@ def _search_loop(engine, px, *, max_length, pad_token_id, eos_token_id, decoder_
         st = {"sequences": torch.full((R, Lmax), pad_token_id, dtype=I32, device=dev),
               "finished": torch.zeros(R, dtype=I32, device=dev), "next_token": next_token, "active": active}
         st["sequences"][:, 0] = decoder_start_token_id
+        key = sample_key
         for cur_len in range(1, Lmax):
             forced = _forced_token(cur_len, Lmax, forced_bos_token_id, forced_eos_token_id)
             last = cur_len == Lmax - 1
+            gk = None
+            if sample_key is not None:
+                # `_sample` :616-625: split the key, draw from the RAW logits (processors / warpers do not act)
+                gk, key = prng_split(key)
+                forced = -1
             if not (last and forced >= 0):
                 hf = _step(engine, cache, st["next_token"], cur_len - 1, active)
             if forced < 0:
                 mt = eos_token_id if (mask_eos and _min_length_applies(cur_len, min_length)) else -1
-                _lm_head_search(engine, cache, hf, mt, ws, active)
+                _lm_head_search(engine, cache, hf, mt, ws, active, gumbel_key=gk)
                 if trace_cb is not None:
                     trace_cb(cur_len, ws, st)
             ops.greedy_step(ws, st, forced, R, Lmax, cur_len, eos_token_id, pad_token_id)
@@ -322,13 +390,16 @@ def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_w
     loop is then captured into ONE CUDA graph and later calls only copy the pixels in and replay it."""
     if kw["num_beams"] > 8:
         raise NotImplementedError("beam search keeps 2*num_beams <= 16 candidates per image row (num_beams <= 8)")
-    px = pixel_values.to(engine.dev, F32).contiguous()
+    px = pixel_values.to(engine.dev).contiguous() if pixel_values.dtype == torch.uint8 else \
+        pixel_values.to(engine.dev, F32).contiguous()
     # parameters are frozen while the loop runs: GEMMs prefetch weight tiles ahead of their dependency wait
     prefetch_weights = pdl if prefetch_weights is None else prefetch_weights
     ops.launch_options(pdl=int(pdl), gemm_b_static=int(prefetch_weights))
     if trace_cb is not None:
         use_cuda_graph = False
         kw = dict(kw, trace_cb=trace_cb)
+    if kw.get("sample_key") is not None:
+        use_cuda_graph = False                  # the per-step keys are launch arguments: a replay would repeat them
     try:
         return _generate(engine, px, use_cuda_graph, (pdl, prefetch_weights), kw)
     finally:
@@ -338,7 +409,7 @@ def generate(engine, pixel_values, *, use_cuda_graph=True, pdl=False, prefetch_w
 def _generate(engine, px, use_cuda_graph, pdl, kw):
     if not use_cuda_graph:
         return _search_loop(engine, px, **kw)
-    key = (tuple(px.shape), pdl) + tuple(sorted(kw.items()))
+    key = (tuple(px.shape), px.dtype, pdl) + tuple(sorted(kw.items()))
     graphs = engine.__dict__.setdefault("_gen_graphs", {})
     entry = graphs.get(key)
     if entry is None:

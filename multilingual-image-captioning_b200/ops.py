@@ -111,10 +111,20 @@ def pack_kmajor_tiles(src, tile_rows, out):
     _call("mic_pack_kmajor_tiles", _p(src), _ld(src), rows, K, tile_rows, _p(out))
 
 
-def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws, second_pass=False, active=None):
+def _gumbel_key(key):
+    """(k0, k1) uint32 pair -> host array for the C-ABI (None = no sampling noise)."""
+    if key is None:
+        return None, None
+    arr = (ctypes.c_uint32 * 2)(int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF)
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def lm_head_search_packed(h_tiles, e_tiles, bias, mask_token, M, V, K, ws, second_pass=False, active=None,
+                          gumbel_key=None):
+    keep, gk = _gumbel_key(gumbel_key)
     _call("mic_lm_head_search_packed", _p(h_tiles), _p(e_tiles), _p(bias), mask_token, M, V, K, _p(ws["pmax"]),
           _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]), _p(ws["last_val"]) if second_pass else None,
-          _p(ws["last_idx"]) if second_pass else None, _p(active))
+          _p(ws["last_idx"]) if second_pass else None, _p(active), gk)
 
 
 def lm_head_ce_stats(h, emb, bias, labels, ws, logits_out=None):
@@ -150,12 +160,13 @@ def lm_head_ce_grad(h, emb, bias, labels, ws, conf, low, dlogits):
           _p(ws["row_w"]), float(conf), float(low), M, V, K, _p(dlogits), _ld(dlogits))
 
 
-def lm_head_search(h, emb, bias, mask_token, ws, second_pass=False, active=None):
+def lm_head_search(h, emb, bias, mask_token, ws, second_pass=False, active=None, gumbel_key=None):
     M, K = h.shape
     V = emb.shape[0]
+    keep, gk = _gumbel_key(gumbel_key)
     _call("mic_lm_head_search", _p(h), _ld(h), _p(emb), _ld(emb), _p(bias), int(mask_token), M, V, K,
           _p(ws["pmax"]), _p(ws["psum"]), _p(ws["cand_val"]), _p(ws["cand_idx"]),
-          _p(ws["last_val"]) if second_pass else None, _p(ws["last_idx"]) if second_pass else None, _p(active))
+          _p(ws["last_val"]) if second_pass else None, _p(ws["last_idx"]) if second_pass else None, _p(active), gk)
 
 
 def search_merge(ws, R, second_pass=False):

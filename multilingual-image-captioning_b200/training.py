@@ -43,6 +43,22 @@ def bucketed_allreduce_sum(flat: torch.Tensor, bucket_elems: int):
         h.wait()
 
 
+class AdamWConfig:
+    """`optax.adamw(learning_rate=..., b1, b2, eps, weight_decay)` as the reference builds it (main.py:629-635): the
+    hyper-parameters only — the update itself is the fused AdamW kernel.  Pass it as `tx=` to TrainState.create."""
+
+    def __init__(self, learning_rate, b1=0.9, b2=0.999, eps=1e-8, weight_decay=0.0):
+        if not callable(learning_rate):
+            lr = float(learning_rate)
+            learning_rate = lambda step: lr         # noqa: E731  (optax accepts a constant or a schedule)
+        self.learning_rate, self.b1, self.b2, self.eps, self.weight_decay = learning_rate, b1, b2, eps, weight_decay
+
+
+def adamw(learning_rate, b1=0.9, b2=0.999, eps=1e-8, weight_decay=0.0):
+    """Drop-in for the `optax.adamw(...)` call of main.py:629-635."""
+    return AdamWConfig(learning_rate, b1, b2, eps, weight_decay)
+
+
 class TrainState:
     """flax TrainState analogue (main.py:247-251,638): params + AdamW state + step, living on the GPU."""
 
@@ -65,16 +81,49 @@ class TrainState:
         self.rank = dist.get_rank() if self.world > 1 else 0
 
     @classmethod
-    def create(cls, apply_fn=None, params=None, tx=None, model=None, **kw):
-        return cls(model, **kw)
+    def create(cls, apply_fn=None, params=None, tx=None, model=None, dropout_rng=None, **kw):
+        """`TrainState.create(apply_fn=model.__call__, params=model.params, tx=adamw, dropout_rng=...)` (main.py:638).
+        `tx` must be an AdamWConfig (mic_b200.adamw(...)): any other optimiser object would be silently replaced by
+        AdamW with different hyper-parameters, so it is refused.  `apply_fn` may be the model's bound `__call__`."""
+        if model is None and apply_fn is not None:
+            model = getattr(apply_fn, "__self__", None)
+        if model is None:
+            raise ValueError("TrainState.create needs `model=` (or `apply_fn=model.__call__`)")
+        if tx is not None:
+            if not isinstance(tx, AdamWConfig):
+                raise TypeError("tx must be mic_b200.adamw(learning_rate, b1, b2, eps, weight_decay): the step runs a fused "
+                                "AdamW kernel, other optax transformations are not supported")
+            kw = dict(dict(b1=tx.b1, b2=tx.b2, eps=tx.eps, weight_decay=tx.weight_decay), **kw)
+            kw.setdefault("learning_rate_fn", tx.learning_rate)
+        elif "learning_rate_fn" not in kw:
+            raise ValueError("TrainState.create needs tx=mic_b200.adamw(...) or learning_rate_fn=")
+        if params is not None:
+            model._use_params_permanently(params)
+        if dropout_rng is not None:
+            kw.setdefault("dropout_seed", _rng_to_int(dropout_rng))
+        return cls(model, kw.pop("learning_rate_fn"), **kw)
 
     @property
     def params(self):
-        return self.store.tree()
+        """The model's parameter tree with the reference's names (live views of the fp32 master buffer)."""
+        return self.model.params
 
     @property
     def opt_state(self):
-        return {"count": self.step, "mu": self.store.tree(self.store.adam_m), "nu": self.store.tree(self.store.adam_v)}
+        """The optax chain state of `optax.adamw` as flax serialises it (main.py:313-314 `to_bytes(state.opt_state)`):
+        (ScaleByAdamState(count, mu, nu), AddDecayedWeightsState(), ScaleByScheduleState(count)) -> maps "0","1","2".
+        mu / nu are live views of the flat Adam buffers with the parameter tree's names.  [MEMORY: optax 0.0.9 chain]"""
+        import numpy as np
+        cnt = np.asarray(self.step, dtype=np.int32)
+        return {"0": {"count": cnt, "mu": self.store.tree(self.store.adam_m), "nu": self.store.tree(self.store.adam_v)},
+                "1": {}, "2": {"count": cnt}}
+
+    def load_opt_state(self, opt_state, step=None):
+        """Inverse of `opt_state` (restore_model_checkpoint main.py:332-346)."""
+        st = opt_state["0"] if "0" in opt_state else opt_state
+        for name, buf in (("mu", self.store.adam_m), ("nu", self.store.adam_v)):
+            _copy_tree_into(self.store.tree(buf), st[name], self.store.device)
+        self.step = int(step if step is not None else st["count"])
 
     def allreduce_grads(self, lo=0, hi=None, async_stream=False):
         """lax.pmean(grad, 'batch') over grad[lo:hi]: SUM over ranks here, the 1/N is folded into the AdamW kernel.
@@ -124,6 +173,77 @@ class TrainState:
                 ops.adamw(s.master[lo:hi], s.adam_m[lo:hi], s.adam_v[lo:hi], s.grad[lo:hi], s.shadow[lo:hi], *hp)
         self.step = t
         return lr
+
+
+def _rng_to_int(rng):
+    """A PRNG key (jax uint32[2], numpy array, torch tensor or int) folded to one seed for the counter-hash dropout."""
+    import numpy as np
+    if hasattr(rng, "detach"):
+        rng = rng.detach().cpu().numpy()
+    a = np.asarray(rng).astype(np.uint64).reshape(-1)
+    v = 0
+    for x in a:
+        v = (v * 1000003 + int(x)) & 0x3FFFFFFF
+    return int(v)
+
+
+def _copy_tree_into(dst, src, device):
+    import numpy as np
+    for k, v in dst.items():
+        if k not in src:
+            raise KeyError(f"missing entry {k}")
+        if isinstance(v, dict):
+            _copy_tree_into(v, src[k], device)
+        else:
+            s = src[k]
+            s = torch.from_numpy(np.ascontiguousarray(s)) if isinstance(s, np.ndarray) else s
+            if tuple(s.shape) != tuple(v.shape):
+                raise ValueError(f"shape mismatch at {k}: {tuple(s.shape)} vs {tuple(v.shape)}")
+            v.copy_(s.to(device, torch.float32))
+
+
+def save_model_checkpoint(model, save_dir, state, with_opt: bool = False, overwrite: bool = False, logger=None, **kwargs):
+    """main.py:299-328: <save_dir>/ckpt-<step-1>/{config.json, flax_model.msgpack[, opt_state.msgpack,
+    training_state.json]} in the reference's own container format (checkpoint.py).  Hub push is out of scope."""
+    import json
+    import os
+    from . import checkpoint as ck
+    ckpt_save_dir = f"{save_dir}/ckpt-{int(state.step) - 1}"
+    if os.path.exists(ckpt_save_dir) and not overwrite:
+        if logger:
+            logger.info("checkpoint exists, skipping overwrite")
+        return ckpt_save_dir
+    model.save_pretrained(ckpt_save_dir, params=state.params)
+    if with_opt:
+        with open(os.path.join(ckpt_save_dir, "opt_state.msgpack"), "wb") as f:
+            f.write(ck.to_bytes(state.opt_state))
+        with open(os.path.join(ckpt_save_dir, "training_state.json"), "w") as f:
+            json.dump({"step": int(state.step)}, f)
+    return ckpt_save_dir
+
+
+def restore_model_checkpoint(save_dir, state, logger=None):
+    """main.py:332-346: returns (params, opt_state, step) restored INTO the structure of `state` (flax from_bytes
+    semantics: the key sets must match)."""
+    import json
+    import os
+    from . import checkpoint as ck
+    with open(os.path.join(save_dir, ck.FLAX_WEIGHTS_NAME), "rb") as f:
+        params = ck.from_bytes(state.params, f.read())
+    with open(os.path.join(save_dir, "opt_state.msgpack"), "rb") as f:
+        opt_state = ck.from_bytes(state.opt_state, f.read())
+    with open(os.path.join(save_dir, "training_state.json")) as f:
+        step = json.load(f)["step"]
+    return params, opt_state, step
+
+
+def rotate_checkpoints(ckpt_dir: str, save_total_limit: int, logger=None):
+    """main.py:348-357."""
+    import shutil
+    from pathlib import Path
+    ckpts = sorted((str(x) for x in Path(ckpt_dir).glob("ckpt-*")), key=lambda x: int(x.split("-")[-1]))
+    for ckpt in ckpts[:-save_total_limit] if save_total_limit > 0 else []:
+        shutil.rmtree(ckpt)
 
 
 _KEYS = ("pixel_values", "decoder_input_ids", "attention_mask", "input_ids")

@@ -151,16 +151,110 @@ def _gen_defaults(config, max_length, pad_token_id, eos_token_id, decoder_start_
 @torch.no_grad()
 def generate(params, pixel_values, config, max_length=None, pad_token_id=None, eos_token_id=None,
              decoder_start_token_id=None, num_beams=None, min_length=None, forced_bos_token_id=None,
-             forced_eos_token_id=None, length_penalty=None, early_stopping=None, return_trace=False):
+             forced_eos_token_id=None, length_penalty=None, early_stopping=None, return_trace=False,
+             do_sample=False, prng_key=None):
     """`generate` (:128-336): encode once (with the int32 pixel cast of encode(), modeling...:330),
     then greedy (num_beams == 1) or beam search."""
     g = _gen_defaults(config, max_length, pad_token_id, eos_token_id, decoder_start_token_id, num_beams,
                       min_length, forced_bos_token_id, forced_eos_token_id, length_penalty, early_stopping)
     p = rm.to_torch_tree(params)
     enc = rm.encode(p, pixel_values, config, int32_cast=True)
+    if do_sample:
+        if g["num_beams"] != 1:
+            raise NotImplementedError("`Beam sampling is currently not implemented.")
+        return _sample(p, enc, config, g, prng_key, return_trace)
     if g["num_beams"] == 1:
         return _greedy_search(p, enc, config, g, return_trace)
     return _beam_search(p, enc, config, g, return_trace)
+
+
+# ----------------------------------------------------------------------------------------------
+# jax._src.random at jax==0.2.16 (requirements.txt:13), restated from the published algorithm [MEMORY, risk U9]:
+# PRNGKey(seed) = uint32[seed >> 32, seed & 0xffffffff]; threefry2x32 (20 rounds); split; random_bits; uniform; gumbel;
+# categorical(key, logits) = argmax(logits + gumbel(key, logits.shape)).
+# ----------------------------------------------------------------------------------------------
+def _threefry2x32(k0, k1, x0, x1):
+    k0, k1 = np.uint32(k0), np.uint32(k1)
+    x0, x1 = x0.astype(np.uint32).copy(), x1.astype(np.uint32).copy()
+    ks = [k0, k1, np.uint32(k0 ^ k1 ^ np.uint32(0x1BD11BDA))]
+    rot = ((13, 15, 26, 6), (17, 29, 16, 24))
+    with np.errstate(over="ignore"):
+        x0 += ks[0]
+        x1 += ks[1]
+        for g in range(5):
+            for r in rot[g & 1]:
+                x0 += x1
+                x1 = (x1 << np.uint32(r)) | (x1 >> np.uint32(32 - r))
+                x1 ^= x0
+            x0 += ks[(g + 1) % 3]
+            x1 += ks[(g + 2) % 3] + np.uint32(g + 1)
+    return x0, x1
+
+
+def threefry_2x32(key, count):
+    """jax `threefry_2x32(keypair, count)`: counts split into halves (odd sizes padded with one 0)."""
+    c = np.asarray(count, dtype=np.uint32).ravel()
+    odd = c.size % 2
+    if odd:
+        c = np.concatenate([c, np.zeros(1, np.uint32)])
+    h = c.size // 2
+    y0, y1 = _threefry2x32(key[0], key[1], c[:h], c[h:])
+    out = np.concatenate([y0, y1])
+    return (out[:-1] if odd else out).reshape(np.shape(count))
+
+
+def prng_key(seed=0):
+    return np.array([(int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF], dtype=np.uint32)
+
+
+def prng_split(key, num=2):
+    return threefry_2x32(key, np.arange(num * 2, dtype=np.uint32)).reshape(num, 2)
+
+
+def gumbel(key, shape):
+    size = int(np.prod(shape))
+    bits = threefry_2x32(key, np.arange(size, dtype=np.uint32)).reshape(shape)
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    tiny = np.finfo(np.float32).tiny
+    u = np.maximum(tiny, f * (np.float32(1.0) - tiny) + tiny).astype(np.float32)
+    return (-np.log(-np.log(u))).astype(np.float32)
+
+
+def categorical(key, logits):
+    return np.argmax(gumbel(key, logits.shape) + logits.astype(np.float32), axis=-1)
+
+
+def _sample(p, enc, config, g, key, return_trace=False):
+    """`_sample` (:537-663).  Quirk reproduced: the processed / warped logits are computed and then IGNORED — the
+    token is drawn from the RAW logits (`jax.random.categorical(prng_key, model_outputs.logits[:, -1])`, :623-625),
+    so forced BOS/EOS, min_length, top-k/top-p and temperature have no effect."""
+    B = enc.shape[0]
+    L, pad, eos = g["max_length"], g["pad_token_id"], g["eos_token_id"]
+    sequences = np.full((B, L), pad, dtype=np.int32)
+    sequences[:, 0] = g["decoder_start_token_id"]
+    finished = np.zeros((B,), dtype=bool)
+    running = sequences[:, 0].copy()
+    cache = DecodeCache(config.mbart_config.decoder_layers)
+    key = prng_key(0) if key is None else np.asarray(key, dtype=np.uint32)
+    cur_len, pos, margins = 1, 0, []
+    while not (cur_len == L or finished.all()):
+        k_use, key = prng_split(key)                                          # :616
+        logits = decode_step(p, running, pos, enc, cache, config)
+        noisy = gumbel(k_use, logits.shape) + logits
+        nxt = np.argmax(noisy, axis=-1).astype(np.int32)
+        if return_trace:
+            srt = np.sort(noisy, axis=-1)
+            margins.append(srt[:, -1] - srt[:, -2])
+        finished = finished | (nxt == eos)
+        nxt = np.where(finished, pad, nxt).astype(np.int32)
+        sequences[:, cur_len] = nxt
+        running = nxt
+        cur_len += 1
+        pos += 1
+    out = {"sequences": sequences}
+    if return_trace:
+        out["margins"] = np.stack(margins, 1) if margins else np.zeros((B, 0), np.float32)
+    return out
 
 
 def _greedy_search(p, enc, config, g, return_trace=False):
