@@ -186,7 +186,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        mic_b200.training.init_distributed(local)
     dev = torch.device("cuda", local)
     peaks, peak_src = load_peaks()
 

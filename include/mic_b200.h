@@ -33,8 +33,12 @@ int mic_abi_version(void);
  *   cudaLaunchAttributeProgrammaticStreamSerialization and call griddepcontrol.wait before touching any buffer,
  *   so their prologue overlaps the previous kernel's tail.  Measured on B200 inside CUDA graphs: no gain
  *   (profiles/r01_pdl_microbench.txt), hence off; the tcgen05 GEMMs never use it.
- * gemm_b_static: reserved (ignored). */
-int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static);
+ * gemm_b_static: reserved (ignored).
+ * gemm_sm_margin (default 0): the persistent tcgen05 GEMMs launched afterwards use #SMs - margin CTAs.  One such CTA
+ *   owns a whole SM (~200 KB of shared memory), so a concurrent NCCL all-reduce (lax.pmean, main.py:698) otherwise
+ *   only makes progress between GEMM kernels; data-parallel training sets a margin for the backward segment that
+ *   runs under the gradient all-reduce. */
+int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static, int gemm_sm_margin);
 
 /* ---- dense contraction ------------------------------------------------------------------------
  * D[M,N] = act(A[M,K] * B[N,K]^T + bias) + residual        (tcgen05/TMEM, TMA-fed, bf16 in, fp32 acc)

@@ -43,6 +43,8 @@ void mic_set_error(const char* fmt, ...);
 struct MicLaunchOptions {
   int pdl;        // launch with cudaLaunchAttributeProgrammaticStreamSerialization
   int static_b;   // GEMM B operands (weights) are not written by any kernel in flight: prefetch before pdl_wait
+  int sm_margin;  // persistent tcgen05 GEMMs leave this many SMs free (their CTAs fill a whole SM: a concurrent NCCL
+                  // all-reduce otherwise only runs in the gaps between GEMM kernels, see training.py)
 };
 extern thread_local MicLaunchOptions g_mic_launch;
 

@@ -216,29 +216,58 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (c < N) {
-    for (int r = r0 + rl; r < r1; r += 8) {
-      float g[8];
-      load8(dY + (long long)r * ldy + c, g);
-      if (drop.seed_ptr) {          // backward of x + dropout(z): dz = dy * mask / (1-p), same mask as forward
-        const uint32_t seed = *drop.seed_ptr + drop.site;
-        const uint32_t base = ((uint32_t)r * (uint32_t)N + (uint32_t)c) >> 1;
+    // 4 rows per trip with every load issued before the first use: a thread otherwise has ONE 16-byte load (two with
+    // U) in flight and the kernel sits at 30-45 % of the HBM rate (profiles/r01q_launches.csv: 120 us for 403 MB)
+    constexpr int UNR = 4;
+    for (int rb = r0 + rl; rb < r1; rb += 8 * UNR) {
+      uint4 gv[UNR], uv[UNR];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bool k0, k1;
-          drop_keep2(base + j, seed, drop.thr16, &k0, &k1);
-          g[2 * j] = k0 ? bf16_round(g[2 * j] * drop.scale) : 0.f;
-          g[2 * j + 1] = k1 ? bf16_round(g[2 * j + 1] * drop.scale) : 0.f;
+      for (int k = 0; k < UNR; ++k) {
+        const int r = rb + 8 * k;
+        gv[k] = make_uint4(0, 0, 0, 0);
+        uv[k] = make_uint4(0, 0, 0, 0);
+        if (r < r1) {
+          gv[k] = *reinterpret_cast<const uint4*>(dY + (long long)r * ldy + c);
+          if (act != MIC_ACT_NONE) uv[k] = *reinterpret_cast<const uint4*>(U + (long long)r * ldu + c);
         }
       }
-      if (act != MIC_ACT_NONE) {
-        float u[8];
-        load8(U + (long long)r * ldu + c, u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = bf16_round(g[j] * act_bwd(u[j], act));
+      for (int k = 0; k < UNR; ++k) {
+        const int r = rb + 8 * k;
+        if (r >= r1) continue;
+        float g[8];
+        {
+          float2 f;
+          f = unpack_bf16(gv[k].x); g[0] = f.x; g[1] = f.y;
+          f = unpack_bf16(gv[k].y); g[2] = f.x; g[3] = f.y;
+          f = unpack_bf16(gv[k].z); g[4] = f.x; g[5] = f.y;
+          f = unpack_bf16(gv[k].w); g[6] = f.x; g[7] = f.y;
+        }
+        if (drop.seed_ptr) {          // backward of x + dropout(z): dz = dy * mask / (1-p), same mask as forward
+          const uint32_t seed = *drop.seed_ptr + drop.site;
+          const uint32_t base = ((uint32_t)r * (uint32_t)N + (uint32_t)c) >> 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bool k0, k1;
+            drop_keep2(base + j, seed, drop.thr16, &k0, &k1);
+            g[2 * j] = k0 ? bf16_round(g[2 * j] * drop.scale) : 0.f;
+            g[2 * j + 1] = k1 ? bf16_round(g[2 * j + 1] * drop.scale) : 0.f;
+          }
+        }
+        if (act != MIC_ACT_NONE) {
+          float u[8];
+          float2 f;
+          f = unpack_bf16(uv[k].x); u[0] = f.x; u[1] = f.y;
+          f = unpack_bf16(uv[k].y); u[2] = f.x; u[3] = f.y;
+          f = unpack_bf16(uv[k].z); u[4] = f.x; u[5] = f.y;
+          f = unpack_bf16(uv[k].w); u[6] = f.x; u[7] = f.y;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = bf16_round(g[j] * act_bwd(u[j], act));
+        }
+        if (dU) store8(dU + (long long)r * lddu + c, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g[j];
       }
-      if (dU) store8(dU + (long long)r * lddu + c, g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += g[j];
     }
   }
   if (!dbias) return;
@@ -755,6 +784,9 @@ extern "C" int mic_layernorm_bwd(void* stream, const void* dy, const void* x, co
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                                  float* workspace, unsigned int* counters, int M, int d) {
   MIC_CHECK_ARG(d % 8 == 0 && d <= 1024 && M > 0, "layernorm_bwd: d=%d must be a multiple of 8 and <= 1024", d);
+  // (a fused single-pass variant - dx + per-CTA partial column sums, then a fold kernel - was built and measured in
+  //  round 2: 71 us + 9 us per LayerNorm against 29 + 25 us for these two kernels; its 173 registers per thread leave one
+  //  CTA per SM and the pass becomes latency-bound, so the two-kernel form stays)
   layernorm_bwd_dx_kernel<<<(M + 7) / 8, 256, 0, STREAM>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
                                                            (const bf16*)dres, (bf16*)dx, M, d);
   MIC_CHECK_LAUNCH();
@@ -920,7 +952,12 @@ extern "C" int mic_adamw(void* stream, float* p, float* m, float* v, const float
   MIC_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
                     ((uintptr_t)g & 15) == 0,
                 "adamw: state pointers must be 16-byte aligned");
-  adamw_kernel<<<grid_for(n / 4 + 1, 256, 16), 256, 0, STREAM>>>(p, m, v, g, (bf16*)shadow_bf16, hyper, n);
+  // grid-stride CTAs live for the whole kernel and 8 of them (2,048 threads) fill an SM: with a communication margin
+  // set (data-parallel step: the next bucket's all-reduce runs concurrently) only 5 CTAs per SM are launched, so an
+  // NCCL CTA always finds room
+  int grid = grid_for(n / 4 + 1, 256, 16);
+  if (g_mic_launch.sm_margin > 0 && grid > mic_num_sms() * 5) grid = mic_num_sms() * 5;
+  adamw_kernel<<<grid, 256, 0, STREAM>>>(p, m, v, g, (bf16*)shadow_bf16, hyper, n);
   MIC_CHECK_LAUNCH();
   return MIC_OK;
 }

@@ -20,10 +20,11 @@ void mic_set_error(const char* fmt, ...) {
 extern "C" const char* mic_last_error(void) { return g_err; }
 extern "C" int mic_abi_version(void) { return MIC_B200_ABI_VERSION; }
 
-thread_local MicLaunchOptions g_mic_launch = {0, 0};   // measured on B200: PDL does not pay inside CUDA graphs (tools/microbench_pdl.py)
-extern "C" int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static) {
+thread_local MicLaunchOptions g_mic_launch = {0, 0, 0};   // measured on B200: PDL does not pay inside CUDA graphs (tools/microbench_pdl.py)
+extern "C" int mic_launch_options(int programmatic_dependent_launch, int gemm_b_static, int gemm_sm_margin) {
   if (programmatic_dependent_launch >= 0) g_mic_launch.pdl = programmatic_dependent_launch != 0;
   if (gemm_b_static >= 0) g_mic_launch.static_b = gemm_b_static != 0;
+  if (gemm_sm_margin >= 0) g_mic_launch.sm_margin = gemm_sm_margin < mic_num_sms() - 8 ? gemm_sm_margin : mic_num_sms() - 8;
   return MIC_OK;
 }
 
@@ -151,7 +152,8 @@ static int launch_one(cudaStream_t stream, const Operands& o, const typename Epi
     attr_set = true;
   }
   const int tiles = o.shape.num_m_blocks * o.shape.num_n_blocks * o.shape.split_k;
-  const int grid = tiles < mic_num_sms() ? tiles : mic_num_sms();
+  const int sms = mic_num_sms() - g_mic_launch.sm_margin;      // SMs left free for a concurrent collective
+  const int grid = tiles < sms ? tiles : sms;
   // (plain launch: the tcgen05 GEMM does not take part in programmatic dependent launch - its producer loop is
   //  kept minimal; a PDL-aware variant with weight prefetch cost the training step 7 %)
   kern<<<grid, Cfg<BN, Epi::NBUF, Epi::EW>::THREADS, Cfg<BN, Epi::NBUF, Epi::EW>::SMEM_BYTES, stream>>>(o.ta, o.tb, o.td, o.td2, o.shape, ep);

@@ -257,9 +257,10 @@ def decoder_step(plan, num_layers, R, pos, sync, phase_times=None, active=None, 
           DECODER_STEP_OPTS[0] if opts is None else int(opts))
 
 
-def launch_options(pdl=-1, gemm_b_static=-1):
-    """mic_launch_options: programmatic dependent launch on/off, weights-are-static hint for the decode loop."""
-    lib().mic_launch_options(int(pdl), int(gemm_b_static))
+def launch_options(pdl=-1, gemm_b_static=-1, gemm_sm_margin=-1):
+    """mic_launch_options: programmatic dependent launch on/off, weights-are-static hint for the decode loop, SMs the
+    persistent GEMMs leave free for a concurrent NCCL collective."""
+    lib().mic_launch_options(int(pdl), int(gemm_b_static), int(gemm_sm_margin))
 
 
 _COUNTERS = {}

@@ -32,6 +32,25 @@ def create_learning_rate_fn(train_ds_size, train_batch_size, num_train_epochs, n
     return schedule
 
 
+def init_distributed(local_rank: int, backend: str = "nccl"):
+    """`torch.distributed` set-up for one process per GPU.  The NCCL streams are HIGH PRIORITY: the gradient all-reduce
+    runs concurrently with backward kernels and must get SM slots as soon as they free up (see `train_step`)."""
+    import os
+    if dist.is_initialized():
+        return
+    if backend == "nccl":
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+        except Exception:           # older torch: plain defaults
+            opts = None
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+    else:
+        dist.init_process_group(backend)
+
+
 def bucketed_allreduce_sum(flat: torch.Tensor, bucket_elems: int):
     """In-place SUM all-reduce of a flat buffer in fixed-size buckets (launch-latency sized, not link sized:
     NVSwitch gives every peer full bandwidth).  Works for any backend (NCCL on GPU, gloo in the CPU tests)."""
@@ -74,6 +93,11 @@ class TrainState:
         self.bucket_elems = max(int(bucket_bytes) // 4, 1)
         self.metrics_buf = torch.zeros(2, dtype=F32, device=self.store.device)
         self.comm_stream = None
+        # SMs the persistent GEMMs of the vision backward (and CTA slots the AdamW kernel) leave free while a gradient
+        # all-reduce is in flight: one tcgen05 GEMM CTA owns a whole SM, so without a margin NCCL's CTAs only run in
+        # the gaps between GEMM kernels (round-2 timeline at 8 GPUs: 1.84 GB took 10.5 ms, the 0.35 GB tail 6.3 ms)
+        import os
+        self.comm_sm_margin = int(os.environ.get("MIC_COMM_SM_MARGIN", "16")) if self.world > 1 else 0
         # train=True semantics (main.py:692): decoder dropout at mbart_config.dropout unless overridden;
         # one fresh mask per step and per rank (dropout_rng split / shard_prng_key, main.py:251,686)
         self.dropout = model.config.mbart_config.dropout if dropout is None else float(dropout)
@@ -125,6 +149,15 @@ class TrainState:
             _copy_tree_into(self.store.tree(buf), st[name], self.store.device)
         self.step = int(step if step is not None else st["count"])
 
+    def _stamp(self, name, stream=None):
+        """Timeline aid (tools/dp_timeline.py): when `self.timeline` is a list, record a timing event on `stream`."""
+        tl = self.__dict__.get("timeline")
+        if tl is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        tl.append((name, ev))
+
     def allreduce_grads(self, lo=0, hi=None, async_stream=False):
         """lax.pmean(grad, 'batch') over grad[lo:hi]: SUM over ranks here, the 1/N is folded into the AdamW kernel.
         async_stream=True issues the collective on a dedicated communication stream that first waits for the
@@ -137,12 +170,14 @@ class TrainState:
             bucketed_allreduce_sum(g[lo:hi], self.bucket_elems)
             return
         if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream(device=self.store.device)
+            self.comm_stream = torch.cuda.Stream(device=self.store.device, priority=-1)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
+            self._stamp(f"allreduce[{lo}:{hi}] start", self.comm_stream)
             bucketed_allreduce_sum(g[lo:hi], self.bucket_elems)
+            self._stamp(f"allreduce[{lo}:{hi}] end", self.comm_stream)
             done = torch.cuda.Event()
             done.record(self.comm_stream)
         return done
@@ -171,6 +206,7 @@ class TrainState:
                 if ev is not None:
                     cur.wait_event(ev)
                 ops.adamw(s.master[lo:hi], s.adam_m[lo:hi], s.adam_v[lo:hi], s.grad[lo:hi], s.shadow[lo:hi], *hp)
+                self._stamp(f"adamw[{lo}:{hi}] end")
         self.step = t
         return lr
 
@@ -317,7 +353,14 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
     stages = (1, 2) if dp else (0,)      # data parallel: two graph segments so the all-reduce can overlap
 
     def run_stage(stage):
-        return eng.forward_backward(*args, label_smoothing=label_smoothing_factor, stage=stage)
+        # stage 2 (vision backward) runs under the all-reduce of everything stage 1 produced: its GEMMs leave
+        # `comm_sm_margin` SMs to NCCL (baked into the captured graph)
+        margin = state.comm_sm_margin if (dp and stage == 2) else 0
+        ops.launch_options(gemm_sm_margin=margin)
+        try:
+            return eng.forward_backward(*args, label_smoothing=label_smoothing_factor, stage=stage)
+        finally:
+            ops.launch_options(gemm_sm_margin=0)
 
     evs = []
 
@@ -360,15 +403,21 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
                     between()
         sb["warm"] = True
     else:
+        state._stamp("step start")
         for i, g in enumerate(sb["graph"]):
             g.replay()
+            state._stamp(f"graph stage {stages[i]} end")
             if stages[i] == 1:
                 between()
         ws = sb["ws"]
     if dp:
         split, n = eng.grad_split_offset(), state.store.grad.numel()
         ev2 = state.allreduce_grads(split, None, async_stream=True)
-        lr = state.apply_gradients([(0, split, evs[-1]), (split, n, ev2)])
+        ops.launch_options(gemm_sm_margin=state.comm_sm_margin)       # AdamW of bucket 1 leaves CTA slots to all-reduce 2
+        try:
+            lr = state.apply_gradients([(0, split, evs[-1]), (split, n, ev2)])
+        finally:
+            ops.launch_options(gemm_sm_margin=0)
     else:
         lr = state.apply_gradients()
     loss = ws["out"][0:1].clone()

@@ -10,7 +10,7 @@ from mic_b200 import synthetic, ops
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+mic_b200.training.init_distributed(local)
 cfg = mic_b200.tiny_config(vocab_size=1003, layers=2)
 params = synthetic.make_params(cfg, seed=1, perturbed=True, std=0.05)
 shards = [synthetic.make_batch(cfg, 4, seq_len=16, seed=10 + r, min_len=3 + 5 * r) for r in range(world)]
