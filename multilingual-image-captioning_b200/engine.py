@@ -457,8 +457,12 @@ class CaptionEngine:
         B, T = decoder_input_ids.shape
         S, dv, d = c.num_tokens, c.hidden_size, t.d_model
         M, Mv = B * T, B * S
-        if stage == 2:
-            return self._backward_vision(B, S, Mv, dv, d)
+        if stage in (2, 3):
+            # data parallel: the vision backward in two segments, so that only the gradients of the last
+            # `dp_vision_tail_layers` encoder layers + the embeddings are all-reduced after the backward has ended
+            L = c.num_hidden_layers
+            k = min(self.dp_vision_tail_layers, L)
+            return self._backward_vision(B, S, Mv, dv, d, part=("head", L - 1, k) if stage == 2 else ("tail", k - 1, 0))
         ids = decoder_input_ids.to(self.dev, I32).contiguous().view(-1)
         km = attention_mask.to(self.dev, I32).contiguous()
         lab = labels.to(self.dev, I32).contiguous().view(-1)
@@ -521,34 +525,55 @@ class CaptionEngine:
         self._backward_vision(B, S, Mv, dv, d)
         return ws
 
+    dp_vision_tail_layers = 4       # encoder layers whose gradients form the last (exposed) all-reduce bucket
+
     def grad_split_offset(self):
         """Flat-buffer offset separating the gradients finished by stage 1 from those of stage 2."""
         return self.ps.layout.storages["proj.w"][0]
 
-    def _backward_vision(self, B, S, Mv, dv, d):
+    def grad_split_offsets(self):
+        """Flat-buffer offsets [after stage 1, after stage 2]: stage 1 = head, tied embedding, decoder, cross K/V;
+        stage 2 = visual projection + the upper vision layers; stage 3 = the rest (the buffer is laid out in backward
+        order for exactly this)."""
+        L = self.c.num_hidden_layers
+        k = min(self.dp_vision_tail_layers, L)
+        second = self.ps.layout.storages[f"v.{k - 1}.fc2.w"][0] if k > 0 else self.ps.layout.storages["v.pre_ln.scale"][0]
+        return [self.ps.layout.storages["proj.w"][0], second]
+
+    def _backward_vision(self, B, S, Mv, dv, d, part=None):
+        """part = None: everything.  ("head", hi, lo): visual projection + final LN + layers hi..lo;
+        ("tail", hi, lo): layers hi..lo + the embeddings (continues from the buffers the head left)."""
         c, t, ps, b = self.c, self.t, self.ps, self.bufs
         enc = b.t["tr.enc.out"]
         d_enc = b.t["tr.d_enc"]
-        # ---------------- backward: visual projection ----------------
         te = "tr.enc"
         L = c.num_hidden_layers
-        x_last = b.t[te + ".post"] if c.final_layernorm else b.t[te + f".x{L}"]
+        do_head = part is None or part[0] == "head"
+        do_tail = part is None or part[0] == "tail"
+        l_hi, l_lo = (L - 1, 0) if part is None else (part[1], part[2])
         dxv = b.get("tr.dxv", (Mv, dv))
-        self._dense_bwd(x_last, d_enc, "proj", dxv)
         dvt = b.get("tr.dvt", (Mv, dv))
         if c.final_layernorm:
-            self._ln_bwd(dxv, b.t[te + f".x{L}"], "v.post_ln", (b.t[te + ".post.mean"], b.t[te + ".post.rstd"]), None, dvt)
-            dxv, dvt = dvt, dxv
-        else:
-            ps.g("v.post_ln.scale").zero_()      # dead parameters (pooled output unused): zero gradient
-            ps.g("v.post_ln.bias").zero_()
+            dxv, dvt = dvt, dxv              # the final-LN backward below leaves the stream gradient in the other buffer
+        if do_head:
+            if c.final_layernorm:
+                dxv, dvt = dvt, dxv
+            # ---------------- backward: visual projection ----------------
+            x_last = b.t[te + ".post"] if c.final_layernorm else b.t[te + f".x{L}"]
+            self._dense_bwd(x_last, d_enc, "proj", dxv)
+            if c.final_layernorm:
+                self._ln_bwd(dxv, b.t[te + f".x{L}"], "v.post_ln", (b.t[te + ".post.mean"], b.t[te + ".post.rstd"]), None, dvt)
+                dxv, dvt = dvt, dxv
+            else:
+                ps.g("v.post_ln.scale").zero_()      # dead parameters (pooled output unused): zero gradient
+                ps.g("v.post_ln.bias").zero_()
         # ---------------- backward: vision layers ----------------
         Hv = c.num_attention_heads
         vscale = 1.0 / math.sqrt(c.head_dim)
         dgv = b.get("tr.dgv", (Mv, c.intermediate_size))
         duv = b.get("tr.duv", (Mv, c.intermediate_size))
         dqkvv = b.get("tr.dqkvv", (Mv, 3 * dv))
-        for l in reversed(range(L)):
+        for l in range(l_hi, l_lo - 1, -1):
             n = f"v.{l}"
             sfx = f".{l}"
             g_, u_, ln2 = b.t[te + ".g" + sfx], b.t[te + ".u" + sfx], b.t[te + ".ln2" + sfx]
@@ -567,6 +592,9 @@ class CaptionEngine:
                               False, dqkvv[:, :dv], dqkvv[:, dv:2 * dv], dqkvv[:, 2 * dv:], B, Hv, S, S, vscale)
             self._dense_bwd(ln1, dqkvv, n + ".qkv", dvt)
             self._ln_bwd(dvt, x0, n + ".ln1", (b.t[te + ".ln1.mean" + sfx], b.t[te + ".ln1.rstd" + sfx]), dxv, dxv)
+        if not do_tail:
+            self._join_side()
+            return None
         # embeddings: pre-LN, class / position / patch kernel
         if c.pre_layernorm:
             demb_v = self._ln_bwd(dxv, b.t[te + ".emb"], "v.pre_ln", (b.t[te + ".pre.mean"], b.t[te + ".pre.rstd"]),

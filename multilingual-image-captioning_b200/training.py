@@ -93,11 +93,12 @@ class TrainState:
         self.bucket_elems = max(int(bucket_bytes) // 4, 1)
         self.metrics_buf = torch.zeros(2, dtype=F32, device=self.store.device)
         self.comm_stream = None
-        # SMs the persistent GEMMs of the vision backward (and CTA slots the AdamW kernel) leave free while a gradient
-        # all-reduce is in flight: one tcgen05 GEMM CTA owns a whole SM, so without a margin NCCL's CTAs only run in
-        # the gaps between GEMM kernels (round-2 timeline at 8 GPUs: 1.84 GB took 10.5 ms, the 0.35 GB tail 6.3 ms)
+        # SMs the persistent GEMMs of the vision backward may leave free while a gradient all-reduce is in flight (one
+        # tcgen05 GEMM CTA owns a whole SM).  Measured at 8 GPUs (profiles/r02_dp_timeline_n8.txt): a margin of 16 / 32
+        # SMs made the step 0.6 / 1.5 ms SLOWER — the all-reduce is not SM-starved but shares HBM and the power budget
+        # with the GEMMs — so the default is 0; the knob stays for other topologies.
         import os
-        self.comm_sm_margin = int(os.environ.get("MIC_COMM_SM_MARGIN", "16")) if self.world > 1 else 0
+        self.comm_sm_margin = int(os.environ.get("MIC_COMM_SM_MARGIN", "0")) if self.world > 1 else 0
         # train=True semantics (main.py:692): decoder dropout at mbart_config.dropout unless overridden;
         # one fresh mask per step and per rank (dropout_rng split / shard_prng_key, main.py:251,686)
         self.dropout = model.config.mbart_config.dropout if dropout is None else float(dropout)
@@ -350,12 +351,18 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
     args = (sb["pixel_values"], sb["decoder_input_ids"], sb["attention_mask"], sb["input_ids"])
     ls = (label_smoothing_factor, state.dropout)
     dp = state.world > 1
-    stages = (1, 2) if dp else (0,)      # data parallel: two graph segments so the all-reduce can overlap
+    # data parallel: three graph segments.  After each one a prefix of the flat gradient buffer is final (it is laid out
+    # in backward order) and its all-reduce starts on the communication stream while the next segment computes:
+    #   1: forward + lm_head/CE + decoder + cross-K/V backward   -> 84 % of the bytes (tied embedding, decoder)
+    #   2: visual projection + upper vision layers               -> 11 %
+    #   3: last `dp_vision_tail_layers` vision layers + embeddings -> 5 %: the only all-reduce nothing can hide
+    stages = (1, 2, 3) if dp else (0,)
+    bounds = ([0] + eng.grad_split_offsets() + [state.store.grad.numel()]) if dp else None
 
     def run_stage(stage):
-        # stage 2 (vision backward) runs under the all-reduce of everything stage 1 produced: its GEMMs leave
-        # `comm_sm_margin` SMs to NCCL (baked into the captured graph)
-        margin = state.comm_sm_margin if (dp and stage == 2) else 0
+        # segments 2 and 3 run under an all-reduce: their GEMMs may leave `comm_sm_margin` SMs to NCCL (baked into the
+        # captured graph; 0 = off, the measured optimum on NVSwitch boxes: profiles/r02_dp_timeline_n8.txt)
+        margin = state.comm_sm_margin if (dp and stage >= 2) else 0
         ops.launch_options(gemm_sm_margin=margin)
         try:
             return eng.forward_backward(*args, label_smoothing=label_smoothing_factor, stage=stage)
@@ -364,26 +371,24 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
 
     evs = []
 
-    def between():
-        # lax.pmean of everything produced so far (lm_head bias, tied embedding, decoder, cross K/V = 84 % of
-        # the bytes) on the communication stream while the vision backward keeps the SMs busy
+    def after(stage):
+        # lax.pmean of everything this segment finished, on the communication stream
         if dp:
-            evs.append(state.allreduce_grads(0, eng.grad_split_offset(), async_stream=True))
+            i = stages.index(stage)
+            evs.append(state.allreduce_grads(bounds[i], bounds[i + 1], async_stream=True))
 
     if not use_cuda_graph:
         ws = None
         for st in stages:
             r = run_stage(st)
             ws = r if r is not None else ws
-            if st == 1:
-                between()
+            after(st)
     elif sb["graph"] is None or sb.get("ls") != ls:
         ws = None
         for st in stages:                                           # eager: allocates all buffers
             r = run_stage(st)
             ws = r if r is not None else ws
-            if st == 1:
-                between()
+            after(st)
         if sb.get("warm"):
             state.wait_comm()
             torch.cuda.synchronize()
@@ -397,27 +402,26 @@ def train_step(state: TrainState, batch, label_smoothing_factor: float = 0.0, us
                 graphs.append(g)
             sb["graph"], sb["ls"] = graphs, ls
             ws = sb["ws"]
+            evs.clear()
             for i, g in enumerate(graphs):
                 g.replay()
-                if stages[i] == 1:
-                    between()
+                after(stages[i])
         sb["warm"] = True
     else:
         state._stamp("step start")
         for i, g in enumerate(sb["graph"]):
             g.replay()
             state._stamp(f"graph stage {stages[i]} end")
-            if stages[i] == 1:
-                between()
+            after(stages[i])
         ws = sb["ws"]
     if dp:
-        split, n = eng.grad_split_offset(), state.store.grad.numel()
-        ev2 = state.allreduce_grads(split, None, async_stream=True)
-        ops.launch_options(gemm_sm_margin=state.comm_sm_margin)       # AdamW of bucket 1 leaves CTA slots to all-reduce 2
-        try:
-            lr = state.apply_gradients([(0, split, evs[-1]), (split, n, ev2)])
-        finally:
-            ops.launch_options(gemm_sm_margin=0)
+        # AdamW streams 16 GB at the full HBM rate: an all-reduce that runs next to it crawls (measured at 8 GPUs: the
+        # 0.35 GB tail took 5-8 ms beside AdamW against 1.0 ms alone).  So the optimiser starts only when the LAST
+        # bucket has arrived — the collectives are serialised on the communication stream, so that event covers all.
+        torch.cuda.current_stream().wait_event(evs[-1])
+        state._stamp("all gradients reduced")
+        lr = state.apply_gradients()
+        state._stamp("adamw end")
     else:
         lr = state.apply_gradients()
     loss = ws["out"][0:1].clone()

@@ -50,6 +50,19 @@ torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / 10], device="cuda", dtype=torch.float64)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+# one compact line per rank: do all GPUs reach the collectives at the same time, or does one straggler gate them?
+names = [n for n, _ in rows[-1]]
+med = [sorted(row[i][1] for row in rows if len(row) == len(names))[len(rows) // 2] for i in range(len(names))]
+mine = torch.tensor(med, dtype=torch.float64, device="cuda")
+allr = [torch.empty_like(mine) for _ in range(world)]
+if world > 1:
+    dist.all_gather(allr, mine)
+else:
+    allr = [mine]
+if rank == 0:
+    print("per-rank medians (ms after step start):")
+    for i, n in enumerate(names):
+        print(f"  {n:48s} " + " ".join(f"{float(a[i]):7.2f}" for a in allr))
 for r in range(world):
     if world > 1:
         dist.barrier()
