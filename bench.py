@@ -196,7 +196,8 @@ def run_ours(args):
     wl_name = ("ViT-B/16 + BART-large (flax_vit_bart variant, 197 visual tokens)" if vit_bart
                else "CLIP-ViT-B/32 + mBART-50") + " training step (fwd+bwd+AdamW), 224x224 images, 64-token captions"
     B, T = args.batch, 64
-    model = mic_b200.FlaxCLIPVisionMBartForConditionalGeneration(cfg, seed=0, device=dev)
+    model_cls = mic_b200.FlaxViTBartForConditionalGeneration if vit_bart else mic_b200.FlaxCLIPVisionMBartForConditionalGeneration
+    model = model_cls(cfg, seed=0, device=dev)
     sched = mic_b200.create_learning_rate_fn(10_000_000, B * world, 7, 1000, 5e-5)
     state = mic_b200.TrainState(model, sched)
     if world > 1:   # identical replicas (state.replicate(), main.py:738)
@@ -285,11 +286,14 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    with_vb = not args.no_vit_bart and not vit_bart
     if rank != 0:
         if not args.no_generate:      # every rank captions its own images; rank 0 reports the aggregate
             gl = bench_generate(model, cfg, peaks, dev)
             t_ms = torch.tensor([gl["ms_per_call"]], dtype=torch.float64, device=dev)
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        if with_vb:
+            bench_vit_bart(dev, world, rank, peaks)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -351,10 +355,55 @@ def run_ours(args):
             gen_line["cpu_baseline"] = {"value": gval, "unit": "captions/s", "cores": gthreads, "kind": "port",
                                         "sample": gsample}
         line["generate"] = gen_line
+    if with_vb:
+        line["vit_bart"] = bench_vit_bart(dev, world, rank, peaks)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_vit_bart(dev, world, rank, peaks, batch=256, steps=5, warmup=3):
+    """BASELINE configs[4]: ViT-B/16 + BART-large (`flax_vit_bart` variant, 197 visual tokens, post-LN decoder) bf16
+    training step, 256 samples per GPU — a secondary line of the same bench run (every rank trains its own shard;
+    gradients all-reduced over NCCL exactly like the headline workload)."""
+    import torch
+    import torch.distributed as dist
+    import mic_b200
+    from mic_b200 import synthetic
+    cfg = mic_b200.vit_bart_config()
+    model = mic_b200.FlaxViTBartForConditionalGeneration(cfg, seed=0, device=dev)
+    state = mic_b200.TrainState(model, mic_b200.create_learning_rate_fn(10_000_000, batch * world, 7, 1000, 5e-5))
+    if world > 1:
+        dist.broadcast(model.store.master, 0)
+        model.store.refresh_shadow()
+    devb = {k: torch.from_numpy(v).to(dev) for k, v in synthetic.make_batch(cfg, batch, 64, seed=2 + rank).items()}
+    for _ in range(warmup):
+        mic_b200.train_step(state, devb)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        _, m = mic_b200.train_step(state, devb)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    value = batch * world / (ms / 1e3)
+    flop = 225.93e9                                   # SURVEY.md 8d: 75.31 GFLOP forward x 3
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    tf = flop * (value / world) / 1e12
+    return {"metric": "vit_bart_train_samples_per_s", "value": value, "unit": "samples/s", "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "n_gpus": world, "dtype": "bf16",
+            "config": {"workload": "ViT-B/16 + BART-large (flax_vit_bart variant, 197 visual tokens) training step "
+                                   "(fwd+bwd+AdamW), 224x224 channel-first images, 64-token captions",
+                       "per_gpu_batch": batch, "dropout": state.dropout},
+            "step_roofline": {"achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "flop_per_sample": flop},
+            "loss_last": float(m["loss"])}
 
 
 def bench_generate(model, cfg, peaks, dev, B=64, reps=5):
@@ -448,11 +497,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-generate", action="store_true", help="(default now) also time beam-4 generation (configs[3])")
     ap.add_argument("--no-generate", action="store_true", help="skip the beam-4 generation leg of the metric")
+    ap.add_argument("--no-vit-bart", action="store_true", help="skip the secondary ViT-B/16 + BART line (configs[4])")
     ap.add_argument("--model", default="clip-mbart", choices=["clip-mbart", "vit-bart"],
                     help="clip-mbart = BASELINE configs[1,2] (default); vit-bart = configs[4]")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.model == "vit-bart":
+        args.no_generate = True          # configs[3] (beam-4, es_XX) is defined on the CLIP-mBART model
     if args.impl == "reference":
         run_reference(args)
     else:

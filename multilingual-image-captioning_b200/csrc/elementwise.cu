@@ -149,15 +149,29 @@ ln_param_grad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     ab[j] = 0.f;
   }
   if (c < d) {
-    for (int r = r0 + rl; r < r1; r += 8) {
-      float g[8], xv[8];
-      load8(dy + (long long)r * d + c, g);
-      load8(x + (long long)r * d + c, xv);
-      const float mu = mean[r], rs = rstd[r];
+    for (int rb = r0 + rl; rb < r1; rb += 16) {           // two rows per trip, all four loads issued up front
+      const int rn = rb + 8;
+      const bool two = rn < r1;
+      float g[8], xv[8], g2[8], xv2[8];
+      load8(dy + (long long)rb * d + c, g);
+      load8(x + (long long)rb * d + c, xv);
+      if (two) {
+        load8(dy + (long long)rn * d + c, g2);
+        load8(x + (long long)rn * d + c, xv2);
+      }
+      const float mu = mean[rb], rs = rstd[rb];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         ag[j] = fmaf(g[j], (xv[j] - mu) * rs, ag[j]);
         ab[j] += g[j];
+      }
+      if (two) {
+        const float mu2 = mean[rn], rs2 = rstd[rn];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ag[j] = fmaf(g2[j], (xv2[j] - mu2) * rs2, ag[j]);
+          ab[j] += g2[j];
+        }
       }
     }
   }
@@ -181,20 +195,22 @@ ln_param_grad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     part[((long long)blockIdx.y * 2 + 1) * d + col] = sb;
   }
   if (last_cta_of_column(counters + blockIdx.x, nch) && col < d) {
-    float sg0 = 0.f, sg1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+    // fixed-order fold with 4 + 4 independent accumulators (one L2 round trip per 4 partials)
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
     int p = 0;
-    for (; p + 1 < nch; p += 2) {
-      sg0 += part[((long long)p * 2 + 0) * d + col];
-      sb0 += part[((long long)p * 2 + 1) * d + col];
-      sg1 += part[((long long)p * 2 + 2) * d + col];
-      sb1 += part[((long long)p * 2 + 3) * d + col];
+    for (; p + 3 < nch; p += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sg[k] += part[((long long)(p + k) * 2 + 0) * d + col];
+        sb[k] += part[((long long)(p + k) * 2 + 1) * d + col];
+      }
     }
-    if (p < nch) {
-      sg0 += part[((long long)p * 2 + 0) * d + col];
-      sb0 += part[((long long)p * 2 + 1) * d + col];
+    for (; p < nch; ++p) {
+      sg[p & 3] += part[((long long)p * 2 + 0) * d + col];
+      sb[p & 3] += part[((long long)p * 2 + 1) * d + col];
     }
-    dgamma[col] = sg0 + sg1;
-    dbeta[col] = sb0 + sb1;
+    dgamma[col] = (sg[0] + sg[1]) + (sg[2] + sg[3]);
+    dbeta[col] = (sb[0] + sb[1]) + (sb[2] + sb[3]);
   }
 }
 
@@ -284,14 +300,18 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dY, long long ldy, const bf16* __
     part[(long long)blockIdx.y * N + col] = s;
   }
   if (last_cta_of_column(counters + blockIdx.x, nch) && col < N) {
-    float s0 = 0.f, s1 = 0.f;
+    // fixed-order fold of the per-chunk partials with 8 independent accumulators (one L2 round trip per 8 partials)
+    float sacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc[k] = 0.f;
     int p = 0;
-    for (; p + 1 < nch; p += 2) {
-      s0 += part[(long long)p * N + col];
-      s1 += part[(long long)(p + 1) * N + col];
+    for (; p + 7 < nch; p += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sacc[k] += part[(long long)(p + k) * N + col];
     }
-    if (p < nch) s0 += part[(long long)p * N + col];
-    dbias[col] = accumulate ? dbias[col] + s0 + s1 : s0 + s1;
+    for (; p < nch; ++p) sacc[p & 7] += part[(long long)p * N + col];
+    const float tot = ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]));
+    dbias[col] = accumulate ? dbias[col] + tot : tot;
   }
 }
 
@@ -764,7 +784,9 @@ extern "C" int mic_residual_ln_fwd(void* stream, float* acc, const float* bias, 
 }
 
 static int pick_chunks(int M, int col_blocks) {
-  int chunks = (2 * mic_num_sms() + col_blocks - 1) / col_blocks;
+  // ~6 CTAs of 256 threads per SM: these passes are HBM-bound and want many warps in flight (2 CTAs per SM, the
+  // round-1 choice, left them at 30-45 % of the HBM rate)
+  int chunks = (6 * mic_num_sms() + col_blocks - 1) / col_blocks;
   const int by_rows = (M + 511) / 512;                    // at most 512 rows (64 iterations per thread) per chunk
   if (chunks < by_rows) chunks = by_rows;
   const int max_chunks = (M + 31) / 32;
