@@ -203,6 +203,10 @@ def run_ours(args):
     if world > 1:   # identical replicas (state.replicate(), main.py:738)
         dist.broadcast(model.store.master, 0)
         model.store.refresh_shadow()
+    # the generation leg is defined on RANDOM-INIT weights (no natural EOS => exactly 63 decode
+    # steps); a few dozen optimiser steps on one fixed batch already teach the model to emit EOS after ~4 tokens, and
+    # the search loop then legitimately ends early (the decode kernels are skipped once every beam has finished)
+    init_master = model.store.master.clone()
     hb = synthetic.make_batch(cfg, B, T, seed=2 + rank)
     host = {k: torch.from_numpy(v).pin_memory() for k, v in hb.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -287,6 +291,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     with_vb = not args.no_vit_bart and not vit_bart
+    if not args.no_generate:
+        model.store.master.copy_(init_master)
+        model.store.refresh_shadow()
+    del init_master
     if rank != 0:
         if not args.no_generate:      # every rank captions its own images; rank 0 reports the aggregate
             gl = bench_generate(model, cfg, peaks, dev)
@@ -428,6 +436,7 @@ def bench_generate(model, cfg, peaks, dev, B=64, reps=5):
     cps = B / (ms / 1e3)
     gbs = GEN_BYTES_PER_64 * (cps / 64) / 1e9
     seq_fused = out.sequences.cpu().numpy()
+    assert (seq_fused != 1).all(), "the benchmark assumes random-init weights: no caption may end before max_length"
     # ---- end to end: host pixels in, host sequences out, every call
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()

@@ -784,9 +784,10 @@ extern "C" int mic_residual_ln_fwd(void* stream, float* acc, const float* bias, 
 }
 
 static int pick_chunks(int M, int col_blocks) {
-  // ~6 CTAs of 256 threads per SM: these passes are HBM-bound and want many warps in flight (2 CTAs per SM, the
-  // round-1 choice, left them at 30-45 % of the HBM rate)
-  int chunks = (6 * mic_num_sms() + col_blocks - 1) / col_blocks;
+  // 2 CTAs of 256 threads per SM.  (6 per SM was measured in round 2: the wide passes gained 10-40 %, the many narrow
+  // ones lost as much to the longer partial fold - act_bwd_colsum 5.35 vs 5.45 ms, ln_param_grad 1.94 vs 1.57 ms per
+  // training step - so the round-1 choice stays.)
+  int chunks = (2 * mic_num_sms() + col_blocks - 1) / col_blocks;
   const int by_rows = (M + 511) / 512;                    // at most 512 rows (64 iterations per thread) per chunk
   if (chunks < by_rows) chunks = by_rows;
   const int max_chunks = (M + 31) / 32;
