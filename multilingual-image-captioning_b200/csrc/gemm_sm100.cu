@@ -304,6 +304,19 @@ static int search_grid(int M) {
   int g = (mic_num_sms() / mb) * mb;
   return g < mb ? mb : g;
 }
+template <class Epi>
+static int launch_search(void* stream, const Operands& o, const EpiSearchParams& ep, int M) {
+  auto kern = gemm_kernel<0, 0, 256, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(o.ta, o.tb, o.td, o.td2,
+                                                                                                   o.shape, ep);
+  MIC_CHECK_LAUNCH();
+  return MIC_OK;
+}
 extern "C" int mic_lm_head_search_num_partials(int M) { return 2 * (search_grid(M) / ((M + BLOCK_M - 1) / BLOCK_M)); }
 
 extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, const void* E, long long lde,
@@ -318,16 +331,8 @@ extern "C" int mic_lm_head_search(void* stream, const void* H, long long ldh, co
   EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, nullptr, nullptr, upper_val, upper_idx, active,
                         gumbel_key != nullptr, gumbel_key ? gumbel_key[0] : 0u, gumbel_key ? gumbel_key[1] : 0u};
   // fixed m-block per CTA: grid is a multiple of num_m_blocks and tiles are rasterised m-fastest
-  auto kern = gemm_kernel<0, 0, 256, EpiSearch>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
-    attr_set = true;
-  }
-  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      o.ta, o.tb, o.td, o.td2, o.shape, ep);
-  MIC_CHECK_LAUNCH();
-  return MIC_OK;
+  // fixed m-block per CTA: grid is a multiple of num_m_blocks and tiles are rasterised m-fastest
+  return gumbel_key ? launch_search<EpiSample>(stream, o, ep, M) : launch_search<EpiSearch>(stream, o, ep, M);
 }
 
 // ---- packed-operand lm_head search: K-major tile images + bulk copies ---------------------------------------
@@ -392,14 +397,5 @@ extern "C" int mic_lm_head_search_packed(void* stream, const void* h_tiles, cons
   EpiSearchParams ep = {bias, mask_token, pmax, psum, cand_val, cand_idx, (const bf16*)h_tiles, (const bf16*)e_tiles,
                         upper_val, upper_idx, active,
                         gumbel_key != nullptr, gumbel_key ? gumbel_key[0] : 0u, gumbel_key ? gumbel_key[1] : 0u};
-  auto kern = gemm_kernel<0, 0, 256, EpiSearchPacked>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
-    attr_set = true;
-  }
-  kern<<<search_grid(M), NUM_THREADS, Cfg<256>::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      o.ta, o.tb, o.td, o.td2, o.shape, ep);
-  MIC_CHECK_LAUNCH();
-  return MIC_OK;
+  return gumbel_key ? launch_search<EpiSamplePacked>(stream, o, ep, M) : launch_search<EpiSearchPacked>(stream, o, ep, M);
 }

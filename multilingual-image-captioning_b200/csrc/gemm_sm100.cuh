@@ -552,7 +552,8 @@ __device__ __forceinline__ float gumbel_at(uint32_t k0, uint32_t k1, unsigned lo
 // The launcher sizes the grid as a multiple of num_m_blocks with group_m == num_m_blocks, so every CTA
 // keeps the SAME m-block for all of its tiles: the running (max, sum) and the running top-8 of a row live
 // in registers across the whole kernel and are written once (partial slot = CTA rank within the m-block).
-struct EpiSearch {
+template <bool kGumbel>
+struct EpiSearchT {
   typedef EpiSearchParams Params;
   static constexpr int NBUF = 1;
   static constexpr int EW = NUM_EPI_WARPS;
@@ -608,7 +609,7 @@ struct EpiSearch {
       for (int j = 0; j < 64; ++j)
         if (!(v[j] < st.uv || (v[j] == st.uv && col0 + j > st.ui))) v[j] = -INFINITY;
     }
-    if (p.gumbel_on) {
+    if constexpr (kGumbel) {            // `_sample`: a separate instantiation, the search kernels carry none of this
       const unsigned long long total = (unsigned long long)s.M * (unsigned long long)s.N;
       const unsigned long long base = (unsigned long long)ctx.row * (unsigned long long)s.N + (unsigned long long)col0;
       if (ctx.row < s.M) {
@@ -707,12 +708,18 @@ struct EpiSearch {
   }
 };
 
-struct EpiSearchPacked : EpiSearch {};
+typedef EpiSearchT<false> EpiSearch;
+struct EpiSearchPacked : EpiSearchT<false> {};
+typedef EpiSearchT<true> EpiSample;                  // + Gumbel noise of jax.random.categorical: row top-1 = the sample
+struct EpiSamplePacked : EpiSearchT<true> {};
 template <class Epi> struct PackedOperands { static constexpr bool value = false; };
 template <class Epi> struct IsSearchEpi { static constexpr bool value = false; };
 template <> struct IsSearchEpi<EpiSearch> { static constexpr bool value = true; };
 template <> struct IsSearchEpi<EpiSearchPacked> { static constexpr bool value = true; };
+template <> struct IsSearchEpi<EpiSample> { static constexpr bool value = true; };
+template <> struct IsSearchEpi<EpiSamplePacked> { static constexpr bool value = true; };
 template <> struct PackedOperands<EpiSearchPacked> { static constexpr bool value = true; };
+template <> struct PackedOperands<EpiSamplePacked> { static constexpr bool value = true; };
 
 // --------------------------------------------------------------------------------------------
 // The kernel
