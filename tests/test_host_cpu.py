@@ -112,3 +112,28 @@ def test_data_parallel_reduction_world_size_2_gloo(tmp_path):
         out, err = p.communicate(timeout=240)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_gradient_buffer_is_laid_out_in_backward_order_for_the_three_dp_segments():
+    """training.train_step all-reduces a PREFIX of the flat gradient after each backward segment (engine.
+    grad_split_offsets): the layout must store, in this order, head + tied embedding + decoder + cross K/V, then the
+    visual projection and the upper vision layers, then the last `dp_vision_tail_layers` layers and the embeddings."""
+    from mic_b200.params import Layout
+    from mic_b200.engine import CaptionEngine
+    lay = Layout(mic_b200.clip_mbart_config())
+    off = {k: v[0] for k, v in lay.storages.items()}
+    k = CaptionEngine.dp_vision_tail_layers
+    s1, s2 = off["proj.w"], off[f"v.{k - 1}.fc2.w"]
+    seg1 = [n for n in lay.order if off[n] < s1]
+    seg2 = [n for n in lay.order if s1 <= off[n] < s2]
+    seg3 = [n for n in lay.order if off[n] >= s2]
+    assert seg1[0] == "flb" and seg1[1] == "shared" and all(n.startswith(("flb", "shared", "d.")) for n in seg1)
+    assert all(n.startswith("proj.") or n.startswith("v.post_ln") or
+               (n.startswith("v.") and n.split(".")[1].isdigit() and int(n.split(".")[1]) >= k) for n in seg2), seg2[:5]
+    assert all((n.split(".")[1].isdigit() and int(n.split(".")[1]) < k) or n.split(".")[1] in ("pre_ln", "pos", "cls", "patch")
+               for n in seg3), seg3
+    # decoder layers appear in backward order (11 first), so their gradients are final in that order
+    dec = [int(n.split(".")[1]) for n in seg1 if n.startswith("d.") and n.split(".")[1].isdigit()]
+    assert dec == sorted(dec, reverse=True)
+    total = lay.size * 4
+    assert 0.80 < s1 * 4 / total < 0.88 and (lay.size - s2) * 4 / total < 0.07
