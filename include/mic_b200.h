@@ -169,8 +169,8 @@ int mic_adamw(void* stream, float* p, float* m, float* v, const float* g, void* 
 int mic_cast_f32_to_bf16(void* stream, const float* in, void* out, long long n);
 
 /* ---- attention ------------------------------------------------------------------------------------
- * FlaxCLIPAttention / FlaxMBartAttention core [E3,D2,D3]: softmax((q/sqrt(hd)) k^T + mask) v for one
- * (batch, head) per CTA; Tq,Tk <= 64, head_dim 64.  Q/K/V/O are strided views [B*T, ld] with head h at
+ * FlaxCLIPAttention / FlaxMBartAttention / FlaxViTSelfAttention core [E3,D2,D3]: softmax((q/sqrt(hd)) k^T + mask) v;
+ * Tq,Tk <= 256, head_dim 64.  Q/K/V/O are strided views [B*T, ld] with head h at
  * column h*64.  key_mask: int [B,Tk] (1 = keep) or null; causal: key j <= query i. lse: [B,H,Tq]. */
 int mic_attention_fwd(void* stream, const void* Q, long long ldq, const void* K, long long ldk, const void* V,
                       long long ldv, void* O, long long ldo, float* lse, const int* key_mask, int causal, int B,
@@ -179,6 +179,11 @@ int mic_attention_bwd(void* stream, const void* Q, long long ldq, const void* K,
                       long long ldv, const void* O, long long ldo, const void* dO, long long lddo, const float* lse,
                       const int* key_mask, int causal, void* dQ, long long lddq, void* dK, long long lddk, void* dV,
                       long long lddv, int B, int H, int Tq, int Tk, int head_dim, float scale);
+/* A/B switch for the two entry points above (process-wide): 0 (default) / 2 = the row-tiled kernels (one warp per
+ * 16-row tile, cp.async operands, any Tq, Tk <= 256); 1 = the one-CTA-per-(batch, head) kernels where they apply
+ * (Tq, Tk <= 64; longer sequences still take the row-tiled kernels). */
+int mic_attention_impl(int impl);
+
 /* cached 1-token attention of decode() modeling_clip_vision_mbart.py:519-651 [G4].  Cache element
  * (row,pos,h,d) at ((row*cache_len+pos)*ldkv + h*64 + d).  ancestors [R,cache_len]: cache row holding
  * position j of row r's beam history (replaces the cache gather of generation_...:945-953); null ->

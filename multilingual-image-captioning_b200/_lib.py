@@ -19,6 +19,7 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "mic_abi_version": [],
     "mic_launch_options": [I, I, I],
+    "mic_attention_impl": [I],
     "mic_decoder_plan_bytes": [I],
     "mic_decoder_packed_bytes": [I, I, I],
     "mic_decoder_pack_weights": [P, P, I, I, I, P],

@@ -370,6 +370,11 @@ def attention_fwd(q, k, v, out, lse, key_mask, causal, B, H, Tq, Tk, scale):
     return out
 
 
+def attention_impl(impl):
+    """0 / 2 = row-tiled kernels (default), 1 = one-CTA-per-head kernels where they apply (<= 64 tokens): A/B switch."""
+    check(lib().mic_attention_impl(int(impl)), "mic_attention_impl")       # no stream argument: a host-side switch
+
+
 def attention_bwd(q, k, v, o, do, lse, key_mask, causal, dq, dk, dv, B, H, Tq, Tk, scale):
     _call("mic_attention_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(do), _ld(do), _p(lse),
           _p(key_mask), int(causal), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv), B, H, Tq, Tk, 64,

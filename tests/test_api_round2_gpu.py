@@ -269,7 +269,9 @@ def test_vit_bart_class_uses_the_reference_parameter_names(tmp_path):
     with torch.no_grad():
         want = rm.forward_logits(rm.to_torch_tree(params), batch["pixel_values"], batch["decoder_input_ids"],
                                  batch["attention_mask"], None, cfg).numpy()
-    assert np.abs(ref_logits - want).max() <= 3e-2 * np.abs(want).max()
+    # bf16 product path vs the fp32 oracle: worst logit of 64k within 4 % of the logit range, rms within 1 %
+    assert np.abs(ref_logits - want).max() <= 4e-2 * np.abs(want).max()
+    assert np.sqrt(((ref_logits - want) ** 2).mean()) <= 1e-2 * np.abs(want).max()
     # live views: writing through the reference-named tree changes the model
     tree["model"]["encoder"]["layernorm"]["scale"].mul_(1.5)
     model.store.refresh_shadow()

@@ -266,8 +266,48 @@ def _ref_attn(q, k, v, key_mask, causal, scale):
 @pytest.mark.parametrize("Tq,Tk,causal,masked", [(64, 64, True, True), (50, 50, False, False), (64, 50, False, False),
                                                  (5, 5, False, False), (16, 16, True, True), (33, 7, False, False),
                                                  (197, 197, False, False), (64, 197, False, False),
-                                                 (130, 100, True, True), (82, 82, False, True), (16, 82, False, False)])
-def test_attention_fwd_bwd(Tq, Tk, causal, masked):
+                                                 (130, 100, True, True), (82, 82, False, True), (16, 82, False, False),
+                                                 (256, 256, True, True), (1, 1, False, False), (200, 17, False, True),
+                                                 (17, 256, False, False), (144, 144, True, False)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_fwd_bwd(Tq, Tk, causal, masked, impl):
+    """impl 0: the row-tiled kernels (default); impl 1: the one-CTA-per-head kernels (<= 64 tokens)."""
+    if impl == 1 and max(Tq, Tk) > 64:
+        pytest.skip("one-CTA-per-head kernels hold at most 64 tokens")
+    ops.attention_impl(impl)
+    try:
+        _attention_fwd_bwd(Tq, Tk, causal, masked)
+    finally:
+        ops.attention_impl(0)
+
+
+def test_attention_fully_masked_rows_are_zero():
+    """A query whose keys are all padded gets a zero output and zero gradients (softmax over nothing) in both kernels."""
+    B, H, hd, T = 2, 2, 64, 48
+    d = H * hd
+    for impl in (0, 1):
+        ops.attention_impl(impl)
+        try:
+            qkv = rnd(B * T, 3 * d, seed=64)
+            km = torch.ones(B, T, dtype=torch.int32)
+            km[1, :] = 0
+            km = km.to(DEV)
+            out = torch.full((B * T, d), 7.0, dtype=BF16, device=DEV)
+            lse = torch.empty(B, H, T, device=DEV)
+            ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, lse, km, False, B, H, T, T, 0.125)
+            dq = torch.full((B * T, d), 7.0, dtype=BF16, device=DEV)
+            dkv = torch.full((B * T, 2 * d), 7.0, dtype=BF16, device=DEV)
+            ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, rnd(B * T, d, seed=65), lse, km, False, dq,
+                              dkv[:, :d], dkv[:, d:], B, H, T, T, 0.125)
+            torch.cuda.synchronize()
+            assert float(out[T:].float().abs().max()) == 0.0
+            assert float(dq[T:].float().abs().max()) == 0.0 and float(dkv[T:].float().abs().max()) == 0.0
+            assert torch.isfinite(out.float()).all() and torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
+        finally:
+            ops.attention_impl(0)
+
+
+def _attention_fwd_bwd(Tq, Tk, causal, masked):
     B, H, hd = 3, 2, 64
     d = H * hd
     qkv = rnd(B * Tq, 3 * d, seed=60) if Tq == Tk else None

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "attention" 2>&1 | tail -15 > gpurun_out/j23_tests.log
+timeout 300 python tools/attn_bench.py > gpurun_out/j23_attn_bench.txt 2>&1
+ATTN_EAGER=1 timeout 900 ncu --section SpeedOfLight --section Occupancy --section WarpStateStats --section MemoryWorkloadAnalysis --clock-control none --kernel-name-base demangled -k regex:attention --csv --page raw --log-file gpurun_out/j23_attn_ncu.csv python tools/attn_bench.py > gpurun_out/j23_ncu.log 2>&1
+cat gpurun_out/j23_tests.log gpurun_out/j23_attn_bench.txt
