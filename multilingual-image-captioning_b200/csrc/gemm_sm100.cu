@@ -254,6 +254,8 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
     ep.act = -act;
     return launch_one<0, 0, 256, EpiStoreActBwd16>(s, o, ep);
   }
+  // 16 epilogue warps (one 64-column group per warp and tile) for the activation epilogues (issue bound); tried for the
+  // residual + dropout epilogues of the short-K GEMMs as well: no gain (profiles/r02_gemm_epilogue_costs.txt)
   if (!a_mn_major && b_mn_major && act != MIC_ACT_NONE && tma && o.bn == 256)
     return launch_one<0, 1, 256, EpiStoreAct16>(s, o, ep);
   if (!a_mn_major && b_mn_major) return launch_bn<0, 1, EpiStore>(s, o, ep);

@@ -77,6 +77,7 @@ struct EpiCtx {
   int row0;      // first global row of the warp's 32-row slab
   int lane;
   uint8_t* stg;  // warp-private staging buffer (1024-byte aligned)
+  int next_col;  // first column of the group this warp handles next in the same tile, or -1 (set by the kernel loop)
   const CUtensorMap* tmap_d;
   const CUtensorMap* tmap_d2;
 };
@@ -136,11 +137,38 @@ struct EpiStoreT {
   static constexpr int NBUF = NBUF_;
   static constexpr int EW = EW_;
   typedef EpiStoreParams Params;
-  struct State {};
+  struct State {
+    uint4 res[8];   // this thread's 64 residual values of the group about to be processed (loaded ahead by group_pre)
+  };
   __device__ static void kernel_begin(const Params&, State&) {}
   __device__ static void kernel_end(const Params&, State&, const Shape&, int, int) {}
   __device__ static void tile_begin(const Params&, State&, const Shape&, int, int, int) {}
   __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
+  // Called one tile ahead by every epilogue warp: pull the residual rows this warp will add in its NEXT tile towards
+  // L2.  The residual read otherwise sits on the epilogue's critical path (HBM latency per 64-column group: +17 us
+  // on a 35 us [16384,1024,1024] GEMM, profiles/r02_gemm_epilogue_costs.txt) while the tensor pipe waits for TMEM.
+  __device__ static void tile_prefetch(const Params& p, const Shape& s, int row, int col_begin, int col_end) {
+    if (!p.residual || ACT_BWD || row >= s.M) return;
+    const bf16* r = p.residual + (long long)row * p.ldr;
+    for (int c = col_begin; c < col_end && c < s.N; c += GROUP_COLS)   // 64 bf16 = one 128-byte line per group
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r + c));
+  }
+
+  // The residual (or saved pre-activation) values of one 64-column group, straight into registers: each lane reads
+  // the 128 contiguous bytes of its own row.  Issued BEFORE the wait on the accumulator (first group of a tile) or at
+  // the start of the previous group's math, so the load latency is off the TMEM-drain critical path; the lines were
+  // pulled into L2 one tile earlier by tile_prefetch.  Safe for in-place use (residual == D): a thread reads exactly
+  // the elements it later overwrites.
+  __device__ static void group_pre(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0) {
+    if (!p.residual || !p.tma_ok) return;
+    const bool row_ok = ctx.row < s.M;
+    const bf16* r = p.residual + (long long)ctx.row * p.ldr + col0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      st.res[u] = make_uint4(0, 0, 0, 0);
+      if (row_ok && col0 + u * 8 < s.N) st.res[u] = *reinterpret_cast<const uint4*>(r + u * 8);
+    }
+  }
 
   // scalar fallback (unaligned outputs / odd N): v = 32 consecutive columns [col0, col0+32) of row `row`
   __device__ static void chunk_scalar(const Params& p, const Shape& s, int row, int col0, const float* v) {
@@ -170,7 +198,7 @@ struct EpiStoreT {
   }
 
   // v: 64 consecutive columns [col0, col0+64) of row ctx.row (fp32 accumulators)
-  __device__ static void group(const Params& p, State&, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+  __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
     if (col0 >= s.N) return;                      // warp-uniform
     if (!p.tma_ok) {
       chunk_scalar(p, s, ctx.row, col0, v);
@@ -179,23 +207,9 @@ struct EpiStoreT {
     }
     const int lane = ctx.lane;
     uint8_t* stg = ctx.stg;
-    // ---- residual tile: coalesced 16-byte loads -> swizzled staging -> registers ----
-    uint4 res[8];
-    if (p.residual) {
-      stg_acquire<0>(lane);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + (lane >> 3), u = lane & 7;
-        const int grow = ctx.row0 + r, c = col0 + u * 8;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (grow < s.M && c < s.N) val = *reinterpret_cast<const uint4*>(p.residual + (long long)grow * p.ldr + c);
-        *reinterpret_cast<uint4*>(stg_addr(stg, r, u)) = val;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int u = 0; u < 8; ++u) res[u] = *reinterpret_cast<const uint4*>(stg_addr(stg, lane, u));
-      __syncwarp();
-    }
+    // ---- residual values: loaded ahead by group_pre (the next group's loads are issued further down, once these
+    // registers have been consumed: live registers stay at accumulators + one residual set) ----
+    uint4 (&res)[8] = st.res;
     // ---- bias (vector loads; N % 8 == 0 on this path so a unit is all-in or all-out) ----
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -278,6 +292,7 @@ struct EpiStoreT {
         f = unpack_bf16(res[u].w); x[6] += f.x; x[7] += f.y;
       }
     }
+    if (ctx.next_col >= 0) group_pre(p, st, s, ctx, ctx.next_col);   // overlaps the packing / staging / TMA store below
     if (!p.d_f32) {
       if (NBUF == 2 && p.D2)
         stg_acquire<1>(lane);
@@ -724,6 +739,11 @@ template <> struct PackedOperands<EpiSamplePacked> { static constexpr bool value
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
+template <class E, class = void>
+struct EpiHasPrefetch { static constexpr bool value = false; };
+template <class E>
+struct EpiHasPrefetch<E, decltype((void)&E::tile_prefetch)> { static constexpr bool value = true; };
+
 template <int A_MN, int B_MN, int BN, class Epi>
 __global__ void __launch_bounds__(128 + Epi::EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -872,12 +892,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t it = 0;
     typename Epi::State st;
     Epi::kernel_begin(ep, st);
+    if constexpr (EpiHasPrefetch<Epi>::value) {
+      if (blockIdx.x < num_units) {
+        const TileCoord t0 = tile_coord(shape, blockIdx.x % num_tiles);
+        Epi::tile_prefetch(ep, shape, t0.m_blk * BLOCK_M + quarter * 32 + lane, t0.n_blk * BN + g_begin * GROUP_COLS,
+                           t0.n_blk * BN + g_end * GROUP_COLS);
+      }
+    }
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
       const TileCoord tc = tile_coord(shape, u % num_tiles);
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       ctx.row0 = tc.m_blk * BLOCK_M + quarter * 32;
       ctx.row = ctx.row0 + lane;
+      if constexpr (EpiHasPrefetch<Epi>::value) {
+        if (u + (int)gridDim.x < num_units) {       // one tile ahead: a whole epilogue of lead time
+          const TileCoord tn = tile_coord(shape, (u + gridDim.x) % num_tiles);
+          Epi::tile_prefetch(ep, shape, tn.m_blk * BLOCK_M + quarter * 32 + lane, tn.n_blk * BN + g_begin * GROUP_COLS,
+                             tn.n_blk * BN + g_end * GROUP_COLS);
+        }
+      }
       Epi::tile_begin(ep, st, shape, ctx.row, tc.m_blk, tc.n_blk);
+      if constexpr (EpiHasPrefetch<Epi>::value) {
+        if (g_begin < g_end) Epi::group_pre(ep, st, shape, ctx, tc.n_blk * BN + g_begin * GROUP_COLS);
+      }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
@@ -892,6 +929,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
+        ctx.next_col = g + 1 < g_end ? tc.n_blk * BN + (g + 1) * GROUP_COLS : -1;
         Epi::group(ep, st, shape, ctx, tc.n_blk * BN + g * GROUP_COLS, v);
       }
       if (g_begin == g_end) {                        // narrow tiles: this warp owns no column group

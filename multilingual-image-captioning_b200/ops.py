@@ -30,6 +30,7 @@ def _s():
 
 TIMED = {}          # C-ABI name -> list of (start, end) CUDA events recorded around each call (bench.py)
 TIMED_FLOPS = {}    # C-ABI name -> list of 2*M*N*K of the same calls (GEMM family only)
+TIMED_SHAPES = []   # (M, N, K, a_mn, b_mn, block_n, split_k, act, accumulate, d_f32) per timed mic_gemm_bf16 call (tools/gemm_table.py)
 
 
 def _call(name, *args):
@@ -88,6 +89,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, a
         act_code, residual, block_n = -ACT[act_bwd[0]], act_bwd[1], 256
     if "mic_gemm_bf16" in TIMED:
         TIMED_FLOPS.setdefault("mic_gemm_bf16", []).append(2.0 * M * N * K)
+        TIMED_SHAPES.append((M, N, K, int(a_mn), int(b_mn), block_n, split_k, act_code, int(accumulate), int(d_f32)))
     _call("mic_gemm_bf16", int(a_mn), int(b_mn), _p(a), _ld(a), _p(b), _ld(b), M, N, K, _p(out), _ld(out),
           int(d_f32), int(accumulate), _p(bias), act_code, _p(pre_act_out), _p(residual),
           _ld(residual) if residual is not None else 0, block_n, group_m, split_k, *_drop(dropout))
