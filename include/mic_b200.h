@@ -155,6 +155,15 @@ int mic_patchify(void* stream, const float* pixels, void* out, int B, int image_
  * fused with the patch gather.  mean3 / std3: HOST pointers to 3 floats (copied into the launch). */
 int mic_patchify_u8(void* stream, const unsigned char* pixels, void* out, int B, int image_size, int patch,
                     int channel_first, int trunc_int, const float* mean3, const float* std3);
+/* Input hand-off, first half [SURVEY 8f-2]: Transform of main.py:165-172 / evaluation.py:33-41 on the raw uint8 CHW
+ * images of torchvision.io.read_image (main.py:224-226): Resize([S], BICUBIC) (shorter edge -> S; torchvision's tensor
+ * path without antialias = ATen upsample_bicubic2d(align_corners=False), clamp, round-half-even) + CenterCrop(S), a
+ * whole batch of differently sized images per launch.  blob: the images back to back, uint8 [3,H_i,W_i] each;
+ * desc: int64 [n,8] = {byte offset in blob, H, W, resized H', resized W', crop top, crop left, 0} (the two integer
+ * formulas of torchvision are evaluated on the host: mic_b200/transforms.py); out: uint8 [n,S,S,3], or [n,3,S,S] with
+ * channel_first (the flax_vit_bart input layout). */
+int mic_resize_crop_u8(void* stream, const unsigned char* blob, const long long* desc, int n, int S, int channel_first,
+                       unsigned char* out);
 int mic_vit_embed_ln_fwd(void* stream, const void* patch_out, const float* patch_bias, const void* cls,
                          const void* pos, const float* gamma, const float* beta, float eps, int use_ln, void* emb,
                          void* y, float* mean, float* rstd, int B, int S, int d);

@@ -17,9 +17,10 @@ _LAZY = {
     "TrainState": ".training", "train_step": ".training", "eval_step": ".training",
     "create_learning_rate_fn": ".training", "adamw": ".training", "AdamWConfig": ".training",
     "save_model_checkpoint": ".training", "restore_model_checkpoint": ".training", "rotate_checkpoints": ".training",
+    "Transform": ".transforms", "BatchTransform": ".transforms",
 }
 _LAZY_MODULES = ("ops", "engine", "generation", "training", "params", "modeling_clip_vision_mbart", "modeling_vit_bart",
-                 "checkpoint", "_lib")
+                 "checkpoint", "transforms", "_lib")
 
 
 def __getattr__(name):

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mic_batch_sum": [P, P, I, I, I, P, L],
     "mic_patchify": [P, P, P, I, I, I, I, I],
     "mic_patchify_u8": [P, P, P, I, I, I, I, I, P, P],
+    "mic_resize_crop_u8": [P, P, P, I, I, I, P],
     "mic_vit_embed_ln_fwd": [P, P, P, P, P, P, P, F, I, P, P, P, P, I, I, I],
     "mic_drop_cls_rows": [P, P, P, I, I, I],
     "mic_adamw": [P, P, P, P, P, P, L, F, F, F, F, F, F, F, F],

@@ -339,6 +339,14 @@ def patchify(pixels, out, B, image_size, patch, channel_first=False, trunc_int=F
     return out
 
 
+def resize_crop_u8(blob, desc, n, size, out, channel_first=False):
+    """Resize([size], BICUBIC) + CenterCrop(size) of n packed uint8 CHW images (desc: int64 [n,8], see mic_b200.h)."""
+    assert blob.dtype == torch.uint8 and out.dtype == torch.uint8 and desc.dtype == torch.int64 and desc.shape == (n, 8)
+    assert blob.is_contiguous() and out.is_contiguous() and desc.is_contiguous()
+    _call("mic_resize_crop_u8", _p(blob), _p(desc), n, size, int(channel_first), _p(out))
+    return out
+
+
 def vit_embed_ln_fwd(patch_out, patch_bias, cls, pos, gamma, beta, eps, use_ln, emb, out, mean, rstd, B, S):
     d = patch_out.shape[1]
     _call("mic_vit_embed_ln_fwd", _p(patch_out), _p(patch_bias), _p(cls), _p(pos), _p(gamma), _p(beta), float(eps),

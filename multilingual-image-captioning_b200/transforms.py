@@ -1,0 +1,118 @@
+"""Input pipeline hand-off: the reference's image `Transform` (`main.py:165-179`,
+`evaluation.py:33-50`) and the pixel half of `collate_fn` (`main.py:493-495`) on the GPU.
+
+Reference, per sample on a DataLoader worker:   read_image -> Resize([S], BICUBIC) -> CenterCrop(S) ->
+ConvertImageDtype(float) -> Normalize(mean, std);  per batch:  stack -> permute(0, 2, 3, 1) -> numpy float32.
+Here the dataset hands over the raw uint8 CHW images and ONE kernel launch (`mic_resize_crop_u8`) produces the uint8
+NHWC batch on the device; `x/255` + `Normalize` are fused into the patch-embedding gather (`mic_patchify_u8`), which the
+model classes run when `pixel_values` is uint8.  Host work per batch: the two integer formulas of torchvision (resized
+size, crop offsets), one pinned staging copy of the encoded-size bytes and one H2D transfer.
+
+`shift_tokens_right` (`main.py:362-369`, called by `collate_fn` at `:514`: shift one to the right, position 0 = pad) is
+re-exported here for collate functions; it stays on the host, as in the reference (128 KB of token ids per batch).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .synthetic import shift_tokens_right  # noqa: F401  (collate helper, host side as in the reference)
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)     # main.py:175
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def resized_size(h: int, w: int, size: int):
+    """torchvision `Resize([size])`: shorter edge -> size, longer edge -> int(size * long / short). Returns (H', W')."""
+    short, long = (w, h) if w <= h else (h, w)
+    new_short, new_long = size, int(size * long / short)
+    new_w, new_h = (new_short, new_long) if w <= h else (new_long, new_short)
+    return new_h, new_w
+
+
+def crop_offsets(h: int, w: int, size: int):
+    """torchvision `CenterCrop(size)` offsets (top, left); Python's round() (half to even), as torchvision uses."""
+    return int(round((h - size) / 2.0)), int(round((w - size) / 2.0))
+
+
+class BatchTransform:
+    """`collate_fn`-level hand-off: a list of raw uint8 CHW images (torch tensors or numpy arrays, any sizes, as
+    `read_image(..., RGB)` returns them) -> uint8 [n, S, S, 3] on the device (or [n, 3, S, S] with channel_first=True,
+    the flax_vit_bart layout), ready to be passed as `pixel_values`.  Staging buffers are reused between calls."""
+
+    def __init__(self, image_size: int, device=None, channel_first: bool = False):
+        self.size = int(image_size)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.channel_first = bool(channel_first)
+        self._pinned = None
+        self._blob = None
+        self._done = None            # event: the previous batch's H2D copy has left the pinned buffer
+
+    def _stage(self, nbytes: int):
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            cap = max(nbytes, 1 << 20) * 5 // 4
+            self._pinned = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self._blob = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        return self._pinned, self._blob
+
+    def describe(self, shapes):
+        """int64 [n, 8] descriptor table of `mic_resize_crop_u8` for images of the given (H, W)."""
+        desc = np.zeros((len(shapes), 8), np.int64)
+        off = 0
+        for i, (h, w) in enumerate(shapes):
+            nh, nw = resized_size(h, w, self.size)
+            top, left = crop_offsets(nh, nw, self.size)
+            desc[i, :7] = (off, h, w, nh, nw, top, left)
+            off += 3 * h * w
+        return desc, off
+
+    def __call__(self, images, out=None):
+        n = len(images)
+        assert n >= 1
+        arrs = []
+        for im in images:
+            a = im.numpy() if isinstance(im, torch.Tensor) else np.asarray(im)
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[0] != 3:
+                raise ValueError(f"expected uint8 [3, H, W] images (read_image(..., RGB)), got {a.dtype} {a.shape}")
+            arrs.append(np.ascontiguousarray(a))
+        desc, total = self.describe([a.shape[1:] for a in arrs])
+        if self._done is not None:
+            self._done.synchronize()
+        pinned, blob = self._stage(total + 8 * desc.size)
+        pv = pinned.numpy()
+        for a, d in zip(arrs, desc):
+            pv[d[0]:d[0] + a.size] = a.reshape(-1)
+        doff = (total + 7) // 8 * 8                                  # descriptor table rides in the same transfer
+        pv[doff:doff + desc.nbytes] = desc.view(np.uint8).reshape(-1)
+        nbytes = doff + desc.nbytes
+        blob[:nbytes].copy_(pinned[:nbytes], non_blocking=True)
+        self._done = torch.cuda.Event()
+        self._done.record()
+        S = self.size
+        shape = (n, 3, S, S) if self.channel_first else (n, S, S, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        assert tuple(out.shape) == shape and out.dtype == torch.uint8
+        ops.resize_crop_u8(blob, blob[doff:nbytes].view(torch.int64).view(n, 8), n, S, out, self.channel_first)
+        self.last_h2d_bytes = nbytes
+        return out
+
+
+class Transform:
+    """Per-image drop-in with the reference's signature (`Transform(image_size)(x)`, `main.py:165-182`): uint8 [3,H,W]
+    -> float32 [3,S,S], resized / cropped / scaled / normalised, as a device tensor.  The batch path (`BatchTransform`
+    + uint8 `pixel_values`) is the fast one; this class exists so that code written against the reference's per-sample
+    transform keeps working and so that the two can be compared value for value."""
+
+    def __init__(self, image_size: int, device=None, mean=CLIP_MEAN, std=CLIP_STD):
+        self.batch = BatchTransform(image_size, device, channel_first=True)
+        dev = self.batch.device
+        self.mean = torch.tensor(mean, dtype=torch.float32, device=dev).view(3, 1, 1)
+        self.std = torch.tensor(std, dtype=torch.float32, device=dev).view(3, 1, 1)
+
+    def __call__(self, x):
+        u8 = self.batch([x])[0]
+        return (u8.to(torch.float32) / 255.0 - self.mean) / self.std
+
+    forward = __call__
