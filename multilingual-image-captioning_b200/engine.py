@@ -525,7 +525,7 @@ class CaptionEngine:
         self._backward_vision(B, S, Mv, dv, d)
         return ws
 
-    dp_vision_tail_layers = 4       # encoder layers whose gradients form the last (exposed) all-reduce bucket
+    dp_vision_tail_layers = 2       # encoder layers whose gradients form the last (exposed) all-reduce bucket
 
     def grad_split_offset(self):
         """Flat-buffer offset separating the gradients finished by stage 1 from those of stage 2."""

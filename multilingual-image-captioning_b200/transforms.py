@@ -13,6 +13,9 @@ re-exported here for collate functions; it stays on the host, as in the referenc
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import torch
 
@@ -48,6 +51,9 @@ class BatchTransform:
         self._pinned = None
         self._blob = None
         self._done = None            # event: the previous batch's H2D copy has left the pinned buffer
+        # packing the raw bytes into the pinned buffer is a memcpy per image (numpy releases the GIL): a few threads
+        # lift it from ~7 GB/s to the host's memory bandwidth
+        self._pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
 
     def _stage(self, nbytes: int):
         if self._pinned is None or self._pinned.numel() < nbytes:
@@ -81,8 +87,12 @@ class BatchTransform:
             self._done.synchronize()
         pinned, blob = self._stage(total + 8 * desc.size)
         pv = pinned.numpy()
-        for a, d in zip(arrs, desc):
-            pv[d[0]:d[0] + a.size] = a.reshape(-1)
+
+        def pack(k):
+            a, off = arrs[k], int(desc[k, 0])
+            pv[off:off + a.size] = a.reshape(-1)
+
+        list(self._pool.map(pack, range(n)))
         doff = (total + 7) // 8 * 8                                  # descriptor table rides in the same transfer
         pv[doff:doff + desc.nbytes] = desc.view(np.uint8).reshape(-1)
         nbytes = doff + desc.nbytes
