@@ -651,6 +651,50 @@ __device__ __forceinline__ void dq_block_any(const AttnArgs& a, const uint32_t (
   else dq_block<NT, false>(a, qf, dof, sK, sV, sMask, key0, row_base, lane, sc2, lse2, dd, dq);
 }
 
+// dQ of one 16-query tile (one warp): Q / dO / O fragments of the tile from shared memory, D = rowsum(dO o O) formed from
+// the fragments themselves (returned in dd for rows g, g+8), all keys walked in 32-wide blocks; the result leaves through
+// `stage` (a 16-row smem tile this warp owns and no longer needs)
+__device__ __forceinline__ void dq_tile_pass(const AttnArgs& a, int b, int h, int row_base, const bf16* qtile, const bf16* dotile,
+                                             const bf16* otile, const bf16* sK, const bf16* sV, const int* km, int Tkp,
+                                             int lane, bf16* stage, float* dd) {
+  const int g = lane >> 2;
+  uint32_t qf[4][4], dof[4][4];
+  dd[0] = dd[1] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t of[4];
+    lda(qtile, 0, kk * 16, lane, qf[kk]);
+    lda(dotile, 0, kk * 16, lane, dof[kk]);
+    lda(otile, 0, kk * 16, lane, of);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {   // fragment registers 0,2 belong to row g, 1,3 to row g+8
+      const float2 x = unpack_bf16(dof[kk][r]), y = unpack_bf16(of[r]);
+      dd[r & 1] += x.x * y.x + x.y * y.y;
+    }
+  }
+  float lse2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], 1);
+    dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], 2);
+    const int row = row_base + g + i * 8;
+    lse2[i] = row < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + row] * LOG2E : 0.f;
+  }
+  float dq[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[nd][j] = 0.f;
+  const float sc2 = a.scale * LOG2E;
+  int kend = Tkp;
+  if (a.causal) kend = min(kend, row_base + 16);
+  int key0 = 0;
+  for (; key0 + 32 <= kend; key0 += 32) dq_block_any<4>(a, qf, dof, sK, sV, km, key0, row_base, lane, sc2, lse2, dd, dq);
+  if (key0 + 16 <= kend) dq_block_any<2>(a, qf, dof, sK, sV, km, key0, row_base, lane, sc2, lse2, dd, dq);
+  const float sc[2] = {a.scale, a.scale};
+  store_tile_rows(dq, sc, stage, a.dQ + ((long long)b * a.Tq) * a.lddq + h * HD, a.lddq, row_base, a.Tq, lane);
+}
+
 __global__ void __launch_bounds__(256, 2) attention_bwd_dq_tiled_kernel(const AttnArgs a, const TileGeom gm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int qrows = gm.per_cta * 16;
@@ -675,44 +719,9 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_dq_tiled_kernel(const At
   __syncthreads();
   const int row_base = q0 + warp * 16;
   if (row_base >= a.Tq) return;
-  const int g = lane >> 2;
-  bf16* qtile = sQ + warp * 16 * LDS;
-  uint32_t qf[4][4], dof[4][4];
-  float dd[2] = {0.f, 0.f};
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    uint32_t of[4];
-    lda(qtile, 0, kk * 16, lane, qf[kk]);
-    lda(sdO + warp * 16 * LDS, 0, kk * 16, lane, dof[kk]);
-    lda(sO + warp * 16 * LDS, 0, kk * 16, lane, of);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {   // fragment registers 0,2 belong to row g, 1,3 to row g+8
-      const float2 x = unpack_bf16(dof[kk][r]), y = unpack_bf16(of[r]);
-      dd[r & 1] += x.x * y.x + x.y * y.y;
-    }
-  }
-  float lse2[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], 1);
-    dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], 2);
-    const int row = row_base + g + i * 8;
-    lse2[i] = row < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + row] * LOG2E : 0.f;
-  }
-  float dq[8][4];
-#pragma unroll
-  for (int nd = 0; nd < 8; ++nd)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dq[nd][j] = 0.f;
-  const float sc2 = a.scale * LOG2E;
-  const int* km = a.key_mask ? sMask : nullptr;
-  int kend = gm.Tkp;
-  if (a.causal) kend = min(kend, row_base + 16);
-  int key0 = 0;
-  for (; key0 + 32 <= kend; key0 += 32) dq_block_any<4>(a, qf, dof, sK, sV, km, key0, row_base, lane, sc2, lse2, dd, dq);
-  if (key0 + 16 <= kend) dq_block_any<2>(a, qf, dof, sK, sV, km, key0, row_base, lane, sc2, lse2, dd, dq);
-  const float sc[2] = {a.scale, a.scale};
-  store_tile_rows(dq, sc, qtile, a.dQ + ((long long)b * a.Tq) * a.lddq + h * HD, a.lddq, row_base, a.Tq, lane);
+  float dd[2];
+  dq_tile_pass(a, b, h, row_base, sQ + warp * 16 * LDS, sdO + warp * 16 * LDS, sO + warp * 16 * LDS, sK, sV,
+               a.key_mask ? sMask : nullptr, gm.Tkp, lane, sQ + warp * 16 * LDS, dd);
 }
 
 // one block of NT*8 queries of the dK/dV pass for a 16-key tile: S^T = K Q^T, dP^T = V dO^T (keys are the rows).
@@ -797,6 +806,29 @@ __device__ __forceinline__ void dkv_block_any(const AttnArgs& a, const bf16* kti
   else dkv_block<NT, false>(a, ktile, vtile, sQ, sdO, sLse2, sD, sMaskTile, q0, key_base, lane, sc2, dk, dv);
 }
 
+// dK / dV of one 16-key tile (one warp): all queries walked in 32-wide blocks; results leave through the warp's own
+// K / V smem tiles
+__device__ __forceinline__ void dkv_tile_pass(const AttnArgs& a, int b, int h, int key_base, bf16* ktile, bf16* vtile,
+                                              const bf16* sQ, const bf16* sdO, const float* sLse2, const float* sD,
+                                              const int* km, int Tqp, int lane) {
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dk[nd][j] = 0.f;
+      dv[nd][j] = 0.f;
+    }
+  const float sc2 = a.scale * LOG2E;
+  int q0 = 0;
+  if (a.causal) q0 = key_base & ~31;   // queries before the tile's first key see none of its keys
+  for (; q0 + 32 <= Tqp; q0 += 32) dkv_block_any<4>(a, ktile, vtile, sQ, sdO, sLse2, sD, km, q0, key_base, lane, sc2, dk, dv);
+  if (q0 + 16 <= Tqp) dkv_block_any<2>(a, ktile, vtile, sQ, sdO, sLse2, sD, km, q0, key_base, lane, sc2, dk, dv);
+  const float one[2] = {1.f, 1.f}, sc[2] = {a.scale, a.scale};
+  store_tile_rows(dk, sc, ktile, a.dK + ((long long)b * a.Tk) * a.lddk + h * HD, a.lddk, key_base, a.Tk, lane);
+  store_tile_rows(dv, one, vtile, a.dV + ((long long)b * a.Tk) * a.lddv + h * HD, a.lddv, key_base, a.Tk, lane);
+}
+
 __global__ void __launch_bounds__(256, 2) attention_bwd_dkv_tiled_kernel(const AttnArgs a, const TileGeom gm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int krows = gm.per_cta * 16;
@@ -858,25 +890,50 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_dkv_tiled_kernel(const A
   __syncthreads();
   const int key_base = k0 + warp * 16;
   if (key_base >= a.Tk) return;
-  bf16* ktile = sK + warp * 16 * LDS;
-  bf16* vtile = sV + warp * 16 * LDS;
-  float dk[8][4], dv[8][4];
-#pragma unroll
-  for (int nd = 0; nd < 8; ++nd)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dk[nd][j] = 0.f;
-      dv[nd][j] = 0.f;
+  dkv_tile_pass(a, b, h, key_base, sK + warp * 16 * LDS, sV + warp * 16 * LDS, sQ, sdO, sLse2, sD,
+                a.key_mask ? sMask + warp * 16 : nullptr, gm.Tqp, lane);
+}
+
+// Backward for sequences of at most 128 tokens (one CTA per (batch, head) covers every tile of both passes): warp w first
+// forms dQ of query tile w, then dK / dV of key tile w, from ONE shared-memory copy of Q, K, V, dO, O - the two-kernel
+// form reads those five tensors twice.  D = rowsum(dO o O) comes out of the dQ pass and crosses to the dK/dV pass
+// through shared memory (the only CTA barrier after the load).
+__global__ void __launch_bounds__(256, 2) attention_bwd_fused_tiled_kernel(const AttnArgs a, const TileGeom gm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sdO = sQ + gm.Tqp * LDS;
+  bf16* sO = sdO + gm.Tqp * LDS;
+  bf16* sK = sO + gm.Tqp * LDS;
+  bf16* sV = sK + gm.Tkp * LDS;
+  float* sLse2 = reinterpret_cast<float*>(sV + gm.Tkp * LDS);
+  float* sD = sLse2 + gm.Tqp;
+  int* sMask = reinterpret_cast<int*>(sD + gm.Tqp);
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  load_rows_async(a.Q + ((long long)b * a.Tq) * a.ldq + h * HD, a.ldq, 0, a.Tq, gm.Tqp, sQ, tid, nthr);
+  load_rows_async(a.dO + ((long long)b * a.Tq) * a.lddo + h * HD, a.lddo, 0, a.Tq, gm.Tqp, sdO, tid, nthr);
+  load_rows_async(a.O + ((long long)b * a.Tq) * a.ldo + h * HD, a.ldo, 0, a.Tq, gm.Tqp, sO, tid, nthr);
+  load_rows_async(a.K + ((long long)b * a.Tk) * a.ldk + h * HD, a.ldk, 0, a.Tk, gm.Tkp, sK, tid, nthr);
+  load_rows_async(a.V + ((long long)b * a.Tk) * a.ldv + h * HD, a.ldv, 0, a.Tk, gm.Tkp, sV, tid, nthr);
+  for (int r = tid; r < gm.Tqp; r += nthr) sLse2[r] = r < a.Tq ? a.lse[((long long)b * a.H + h) * a.Tq + r] * LOG2E : 0.f;
+  if (a.key_mask)
+    for (int j = tid; j < gm.Tkp; j += nthr) sMask[j] = j < a.Tk ? a.key_mask[(long long)b * a.Tk + j] : 0;
+  cp_async_wait_all();
+  __syncthreads();
+  const int base = warp * 16;
+  if (base < a.Tq) {
+    float dd[2];
+    dq_tile_pass(a, b, h, base, sQ + base * LDS, sdO + base * LDS, sO + base * LDS, sK, sV, a.key_mask ? sMask : nullptr,
+                 gm.Tkp, lane, sO + base * LDS, dd);      // staged through the warp's O rows: Q stays for the second pass
+    if ((lane & 3) == 0) {
+      sD[base + (lane >> 2)] = dd[0];
+      sD[base + (lane >> 2) + 8] = dd[1];
     }
-  const float sc2 = a.scale * LOG2E;
-  const int* km = a.key_mask ? sMask + warp * 16 : nullptr;
-  int q0 = 0;
-  if (a.causal) q0 = key_base & ~31;   // queries before the tile's first key see none of its keys
-  for (; q0 + 32 <= gm.Tqp; q0 += 32) dkv_block_any<4>(a, ktile, vtile, sQ, sdO, sLse2, sD, km, q0, key_base, lane, sc2, dk, dv);
-  if (q0 + 16 <= gm.Tqp) dkv_block_any<2>(a, ktile, vtile, sQ, sdO, sLse2, sD, km, q0, key_base, lane, sc2, dk, dv);
-  const float one[2] = {1.f, 1.f}, sc[2] = {a.scale, a.scale};
-  store_tile_rows(dk, sc, ktile, a.dK + ((long long)b * a.Tk) * a.lddk + h * HD, a.lddk, key_base, a.Tk, lane);
-  store_tile_rows(dv, one, vtile, a.dV + ((long long)b * a.Tk) * a.lddv + h * HD, a.lddv, key_base, a.Tk, lane);
+  }
+  __syncthreads();      // D complete; every warp is done reading K / V as dQ operands
+  if (base < a.Tk)
+    dkv_tile_pass(a, b, h, base, sK + base * LDS, sV + base * LDS, sQ, sdO, sLse2, sD, a.key_mask ? sMask + base : nullptr,
+                  gm.Tqp, lane);
 }
 
 // Cached decode attention: one warp per (row, head); body shared with the persistent decoder-step kernel
@@ -902,7 +959,8 @@ static int check_attn(int head_dim, int Tq, int Tk) {
                 Tk);
   return MIC_OK;
 }
-static int g_attn_impl = 0;   // 0 / 2: row-tiled kernels; 1: one-CTA-per-head kernels where they apply (<= 64 tokens)
+static int g_attn_impl = 0;   // 0: row-tiled kernels (backward fused into one kernel up to 128 tokens); 1: one-CTA-per-head
+                              // kernels where they apply (<= 64 tokens); 2: row-tiled with the backward always as two kernels
 extern "C" int mic_attention_impl(int impl) {
   MIC_CHECK_ARG(impl >= 0 && impl <= 2, "attention impl %d not in [0,2]", impl);
   g_attn_impl = impl;
@@ -974,7 +1032,14 @@ extern "C" int mic_attention_bwd(void* stream, const void* Q, long long ldq, con
   a.dO = (const bf16*)dO; a.lddo = lddo;
   a.dQ = (bf16*)dQ; a.dK = (bf16*)dK; a.dV = (bf16*)dV;
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
-  if (use_tiled(Tq, Tk)) {
+  if (use_tiled(Tq, Tk) && Tq <= 128 && Tk <= 128 && g_attn_impl != 2) {
+    TileGeom gm = tile_geom(Tq, Tk, Tq > Tk ? Tq : Tk);      // one CTA per (batch, head): warps = max(query, key tiles)
+    const int smem = (3 * gm.Tqp + 2 * gm.Tkp) * LDS * 2 + 2 * gm.Tqp * 4 + gm.Tkp * 4;
+    static int have = 0;
+    rc = ensure_smem(attention_bwd_fused_tiled_kernel, smem, &have);
+    if (rc) return rc;
+    attention_bwd_fused_tiled_kernel<<<B * H, gm.per_cta * 32, smem, STREAM>>>(a, gm);
+  } else if (use_tiled(Tq, Tk)) {
     const TileGeom gq = tile_geom(Tq, Tk, Tq), gk = tile_geom(Tq, Tk, Tk);
     const int smem_dq = (3 * gq.per_cta * 16 + 2 * gq.Tkp) * LDS * 2 + gq.Tkp * 4;
     const int smem_dkv = (2 * gk.per_cta * 16 + 2 * gk.Tqp) * LDS * 2 + 2 * gk.Tqp * 4 + gk.per_cta * 16 * 4;

@@ -381,7 +381,8 @@ def attention_fwd(q, k, v, out, lse, key_mask, causal, B, H, Tq, Tk, scale):
 
 
 def attention_impl(impl):
-    """0 / 2 = row-tiled kernels (default), 1 = one-CTA-per-head kernels where they apply (<= 64 tokens): A/B switch."""
+    """A/B switch: 0 = row-tiled kernels (default; fused backward up to 128 tokens), 1 = one-CTA-per-head kernels where
+    they apply (<= 64 tokens), 2 = row-tiled with the backward always as two kernels."""
     check(lib().mic_attention_impl(int(impl)), "mic_attention_impl")       # no stream argument: a host-side switch
 
 

@@ -269,9 +269,10 @@ def _ref_attn(q, k, v, key_mask, causal, scale):
                                                  (130, 100, True, True), (82, 82, False, True), (16, 82, False, False),
                                                  (256, 256, True, True), (1, 1, False, False), (200, 17, False, True),
                                                  (17, 256, False, False), (144, 144, True, False)])
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attention_fwd_bwd(Tq, Tk, causal, masked, impl):
-    """impl 0: the row-tiled kernels (default); impl 1: the one-CTA-per-head kernels (<= 64 tokens)."""
+    """impl 0: the row-tiled kernels (default; backward fused into one kernel up to 128 tokens); impl 1: the
+    one-CTA-per-head kernels (<= 64 tokens); impl 2: row-tiled with the backward always as dQ + dK/dV kernels."""
     if impl == 1 and max(Tq, Tk) > 64:
         pytest.skip("one-CTA-per-head kernels hold at most 64 tokens")
     ops.attention_impl(impl)
@@ -285,7 +286,7 @@ def test_attention_fully_masked_rows_are_zero():
     """A query whose keys are all padded gets a zero output and zero gradients (softmax over nothing) in both kernels."""
     B, H, hd, T = 2, 2, 64, 48
     d = H * hd
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         ops.attention_impl(impl)
         try:
             qkv = rnd(B * T, 3 * d, seed=64)

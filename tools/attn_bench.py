@@ -1,5 +1,5 @@
 """Attention kernel A/B: one-CTA-per-head kernels (impl 1, <= 64 tokens) / previous general kernels vs the row-tiled
-kernels (impl 2) at the shapes of the two models, timed with CUDA events over inputs larger than L2.
+kernels (impl 2: two-kernel backward; impl 0: default, fused backward up to 128 tokens) at the shapes of the two models, timed with CUDA events over inputs larger than L2.
 
     python tools/attn_bench.py            # prints a table; copy to profiles/
 """
@@ -67,10 +67,12 @@ def main():
         flops_f = 4.0 * B * H * Tq * Tk * 64 * (0.5 if causal else 1.0)
         bytes_f = 2.0 * (2 * B * Tq * d + 2 * B * Tk * d)
         bytes_b = 2.0 * (4 * B * Tq * d + 4 * B * Tk * d)
-        for impl in (1, 2):
+        for impl in (1, 2, 0):
             if impl == 1 and max(Tq, Tk) > 64:
                 continue                      # the one-CTA-per-head kernels hold at most 64 tokens
-            impl_name = "1cta" if impl == 1 else "tiled"
+            if impl == 0 and max(Tq, Tk) > 128:
+                continue                      # same kernels as impl 2 beyond 128 tokens
+            impl_name = {1: "1cta", 2: "tiled2", 0: "tiled"}[impl]      # tiled2: backward as dQ + dK/dV kernels
             ops.attention_impl(impl)
             st = {"i": 0}
 
