@@ -33,7 +33,9 @@ def main(path, which=0, out=None):
     per = load(path)
     starts = [i for i, (n, _) in enumerate(per) if "patchify" in n]
     ends = [i for i, (n, _) in enumerate(per) if "adamw" in n]
-    a, b = starts[which], ends[which] + 1
+    # the capture window (-s / -c) starts anywhere: take the which-th patchify that has an adamw after it
+    pairs = [(i, min(e for e in ends if e > i)) for i in starts if any(e > i for e in ends)]
+    a, b = pairs[which][0], pairs[which][1] + 1
     step = per[a:b]
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot = 0.0
