@@ -36,5 +36,34 @@ if what in ("all", "gen"):
     model.engine.__dict__.pop("_gen_graphs", None)
     c = model.generate(batch["pixel_values"], **kw).sequences.cpu().numpy()      # per-op decode path
     print("beam fused", a[0].tolist(), "per-op", c[0].tolist(), "greedy", g[0].tolist())
+if what in ("all", "attn"):
+    # row-tiled attention (forward, fused backward <= 128 tokens, dQ + dK/dV kernels beyond), masked / causal / ragged
+    # shapes, and the image transform: the kernels added after the first sanitizer pass of this round
+    from mic_b200 import ops, transforms
+    dev = "cuda:0"
+    for (Tq, Tk, causal, masked) in [(50, 50, False, False), (64, 64, True, True), (64, 50, False, False),
+                                     (197, 197, False, False), (64, 197, False, True), (130, 100, True, True), (5, 5, False, False)]:
+        B, H, d = 2, 2, 128
+        q = torch.randn(B * Tq, d, device=dev).bfloat16()
+        kv = torch.randn(B * Tk, 2 * d, device=dev).bfloat16()
+        km = None
+        if masked:
+            km = torch.ones(B, Tk, dtype=torch.int32, device=dev)
+            km[0, Tk // 2:] = 0
+        o = torch.empty_like(q)
+        lse = torch.empty(B, H, Tq, device=dev)
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        for impl in (0, 2):
+            ops.attention_impl(impl)
+            ops.attention_fwd(q, kv[:, :d], kv[:, d:], o, lse, km, causal, B, H, Tq, Tk, 0.125)
+            ops.attention_bwd(q, kv[:, :d], kv[:, d:], o, torch.randn_like(q), lse, km, causal, dq, dkv[:, :d], dkv[:, d:],
+                              B, H, Tq, Tk, 0.125)
+        ops.attention_impl(0)
+        assert torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
+    rng = np.random.RandomState(0)
+    imgs = [rng.randint(0, 256, (3, h, w)).astype(np.uint8) for h, w in [(41, 67), (90, 33), (32, 32), (5, 200)]]
+    for cf in (False, True):
+        u8 = transforms.BatchTransform(32, dev, channel_first=cf)(imgs)
+    print("attention + transform ok", tuple(u8.shape))
 torch.cuda.synchronize()
 print("sanitize_run ok")
