@@ -189,9 +189,9 @@ int mic_attention_bwd(void* stream, const void* Q, long long ldq, const void* K,
                       const int* key_mask, int causal, void* dQ, long long lddq, void* dK, long long lddk, void* dV,
                       long long lddv, int B, int H, int Tq, int Tk, int head_dim, float scale);
 /* A/B switch for the two entry points above (process-wide): 0 (default) = the row-tiled kernels (one warp per 16-row
- * tile, cp.async operands, any Tq, Tk <= 256; the backward is ONE kernel when both lengths are <= 128, a dQ and a
- * dK/dV kernel beyond); 1 = the one-CTA-per-(batch, head) kernels where they apply (Tq, Tk <= 64; longer sequences
- * still take the row-tiled kernels); 2 = row-tiled with the backward always as two kernels. */
+ * tile, cp.async operands, any Tq, Tk <= 256; the backward is ONE kernel: dQ pass then dK/dV pass per warp); 1 = the
+ * one-CTA-per-(batch, head) kernels where they apply (Tq, Tk <= 64; longer sequences still take the row-tiled
+ * kernels); 2 = row-tiled with the backward as a dQ and a dK/dV kernel. */
 int mic_attention_impl(int impl);
 
 /* cached 1-token attention of decode() modeling_clip_vision_mbart.py:519-651 [G4].  Cache element

@@ -894,11 +894,12 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_dkv_tiled_kernel(const A
                 a.key_mask ? sMask + warp * 16 : nullptr, gm.Tqp, lane);
 }
 
-// Backward for sequences of at most 128 tokens (one CTA per (batch, head) covers every tile of both passes): warp w first
+// Single-kernel backward (one CTA per (batch, head) covers every tile of both passes; measured against the two-kernel
+// form: 119 -> 82 us at 64 tokens, 509 -> 499 us at 197 tokens, profiles/r02_attention_ab.txt): warp w first
 // forms dQ of query tile w, then dK / dV of key tile w, from ONE shared-memory copy of Q, K, V, dO, O - the two-kernel
 // form reads those five tensors twice.  D = rowsum(dO o O) comes out of the dQ pass and crosses to the dK/dV pass
 // through shared memory (the only CTA barrier after the load).
-__global__ void __launch_bounds__(256, 2) attention_bwd_fused_tiled_kernel(const AttnArgs a, const TileGeom gm) {
+__device__ __forceinline__ void attention_bwd_fused_body(const AttnArgs& a, const TileGeom& gm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sdO = sQ + gm.Tqp * LDS;
@@ -935,6 +936,13 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_fused_tiled_kernel(const
     dkv_tile_pass(a, b, h, base, sK + base * LDS, sV + base * LDS, sQ, sdO, sLse2, sD, a.key_mask ? sMask + base : nullptr,
                   gm.Tqp, lane);
 }
+__global__ void __launch_bounds__(256, 2) attention_bwd_fused_tiled_kernel(const AttnArgs a, const TileGeom gm) {
+  attention_bwd_fused_body(a, gm);
+}
+// up to 16 tiles per sequence (<= 256 tokens: ViT-B/16's 197 -> 13 warps), one CTA per SM
+__global__ void __launch_bounds__(512, 1) attention_bwd_fused_tiled_wide_kernel(const AttnArgs a, const TileGeom gm) {
+  attention_bwd_fused_body(a, gm);
+}
 
 // Cached decode attention: one warp per (row, head); body shared with the persistent decoder-step kernel
 // (decode_device.cuh).
@@ -959,8 +967,8 @@ static int check_attn(int head_dim, int Tq, int Tk) {
                 Tk);
   return MIC_OK;
 }
-static int g_attn_impl = 0;   // 0: row-tiled kernels (backward fused into one kernel up to 128 tokens); 1: one-CTA-per-head
-                              // kernels where they apply (<= 64 tokens); 2: row-tiled with the backward always as two kernels
+static int g_attn_impl = 0;   // 0: row-tiled kernels, single-kernel backward; 1: one-CTA-per-head kernels where they apply
+                              // (<= 64 tokens); 2: row-tiled with the backward as a dQ and a dK/dV kernel
 extern "C" int mic_attention_impl(int impl) {
   MIC_CHECK_ARG(impl >= 0 && impl <= 2, "attention impl %d not in [0,2]", impl);
   g_attn_impl = impl;
@@ -1032,13 +1040,22 @@ extern "C" int mic_attention_bwd(void* stream, const void* Q, long long ldq, con
   a.dO = (const bf16*)dO; a.lddo = lddo;
   a.dQ = (bf16*)dQ; a.dK = (bf16*)dK; a.dV = (bf16*)dV;
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
-  if (use_tiled(Tq, Tk) && Tq <= 128 && Tk <= 128 && g_attn_impl != 2) {
+  if (use_tiled(Tq, Tk) && g_attn_impl != 2) {
     TileGeom gm = tile_geom(Tq, Tk, Tq > Tk ? Tq : Tk);      // one CTA per (batch, head): warps = max(query, key tiles)
+    gm.nsplit = 1;
+    gm.per_cta = ((Tq > Tk ? Tq : Tk) + 15) / 16;
     const int smem = (3 * gm.Tqp + 2 * gm.Tkp) * LDS * 2 + 2 * gm.Tqp * 4 + gm.Tkp * 4;
-    static int have = 0;
-    rc = ensure_smem(attention_bwd_fused_tiled_kernel, smem, &have);
-    if (rc) return rc;
-    attention_bwd_fused_tiled_kernel<<<B * H, gm.per_cta * 32, smem, STREAM>>>(a, gm);
+    if (gm.per_cta <= 8) {
+      static int have = 0;
+      rc = ensure_smem(attention_bwd_fused_tiled_kernel, smem, &have);
+      if (rc) return rc;
+      attention_bwd_fused_tiled_kernel<<<B * H, gm.per_cta * 32, smem, STREAM>>>(a, gm);
+    } else {
+      static int have_w = 0;
+      rc = ensure_smem(attention_bwd_fused_tiled_wide_kernel, smem, &have_w);
+      if (rc) return rc;
+      attention_bwd_fused_tiled_wide_kernel<<<B * H, gm.per_cta * 32, smem, STREAM>>>(a, gm);
+    }
   } else if (use_tiled(Tq, Tk)) {
     const TileGeom gq = tile_geom(Tq, Tk, Tq), gk = tile_geom(Tq, Tk, Tk);
     const int smem_dq = (3 * gq.per_cta * 16 + 2 * gq.Tkp) * LDS * 2 + gq.Tkp * 4;

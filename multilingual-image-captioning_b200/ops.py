@@ -381,8 +381,8 @@ def attention_fwd(q, k, v, out, lse, key_mask, causal, B, H, Tq, Tk, scale):
 
 
 def attention_impl(impl):
-    """A/B switch: 0 = row-tiled kernels (default; fused backward up to 128 tokens), 1 = one-CTA-per-head kernels where
-    they apply (<= 64 tokens), 2 = row-tiled with the backward always as two kernels."""
+    """A/B switch: 0 = row-tiled kernels (default; single-kernel backward), 1 = one-CTA-per-head kernels where they
+    apply (<= 64 tokens), 2 = row-tiled with the backward as a dQ and a dK/dV kernel."""
     check(lib().mic_attention_impl(int(impl)), "mic_attention_impl")       # no stream argument: a host-side switch
 
 

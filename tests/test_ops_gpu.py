@@ -271,8 +271,8 @@ def _ref_attn(q, k, v, key_mask, causal, scale):
                                                  (17, 256, False, False), (144, 144, True, False)])
 @pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attention_fwd_bwd(Tq, Tk, causal, masked, impl):
-    """impl 0: the row-tiled kernels (default; backward fused into one kernel up to 128 tokens); impl 1: the
-    one-CTA-per-head kernels (<= 64 tokens); impl 2: row-tiled with the backward always as dQ + dK/dV kernels."""
+    """impl 0: the row-tiled kernels (default; single-kernel backward); impl 1: the one-CTA-per-head kernels
+    (<= 64 tokens); impl 2: row-tiled with the backward as dQ + dK/dV kernels."""
     if impl == 1 and max(Tq, Tk) > 64:
         pytest.skip("one-CTA-per-head kernels hold at most 64 tokens")
     ops.attention_impl(impl)

@@ -1,5 +1,5 @@
 """Attention kernel A/B: one-CTA-per-head kernels (impl 1, <= 64 tokens) / previous general kernels vs the row-tiled
-kernels (impl 2: two-kernel backward; impl 0: default, fused backward up to 128 tokens) at the shapes of the two models, timed with CUDA events over inputs larger than L2.
+kernels (impl 2: two-kernel backward; impl 0: default, single-kernel backward) at the shapes of the two models, timed with CUDA events over inputs larger than L2.
 
     python tools/attn_bench.py            # prints a table; copy to profiles/
 """
@@ -70,8 +70,6 @@ def main():
         for impl in (1, 2, 0):
             if impl == 1 and max(Tq, Tk) > 64:
                 continue                      # the one-CTA-per-head kernels hold at most 64 tokens
-            if impl == 0 and max(Tq, Tk) > 128:
-                continue                      # same kernels as impl 2 beyond 128 tokens
             impl_name = {1: "1cta", 2: "tiled2", 0: "tiled"}[impl]      # tiled2: backward as dQ + dK/dV kernels
             ops.attention_impl(impl)
             st = {"i": 0}
