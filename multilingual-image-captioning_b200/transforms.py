@@ -48,19 +48,27 @@ class BatchTransform:
         self.size = int(image_size)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.channel_first = bool(channel_first)
-        self._pinned = None
-        self._blob = None
-        self._done = None            # event: the previous batch's H2D copy has left the pinned buffer
+        # two staging slots (pinned host + device blob each) and a copy stream: the H2D transfer of batch i+1 runs
+        # while batch i is still being consumed by the compute stream (resize kernel, training step)
+        self._slots = [{"pinned": None, "blob": None, "copied": None, "consumed": None} for _ in range(2)]
+        self._slot = 0
+        self._copy_stream = torch.cuda.Stream(device=self.device)
         # packing the raw bytes into the pinned buffer is a memcpy per image (numpy releases the GIL): a few threads
         # lift it from ~7 GB/s to the host's memory bandwidth
         self._pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
 
     def _stage(self, nbytes: int):
-        if self._pinned is None or self._pinned.numel() < nbytes:
+        self._slot ^= 1
+        sl = self._slots[self._slot]
+        if sl["copied"] is not None:
+            sl["copied"].synchronize()          # the previous H2D out of this pinned buffer has finished
+        if sl["pinned"] is None or sl["pinned"].numel() < nbytes:
+            if sl["consumed"] is not None:
+                sl["consumed"].synchronize()    # nobody still reads the old device blob
             cap = max(nbytes, 1 << 20) * 5 // 4
-            self._pinned = torch.empty(cap, dtype=torch.uint8).pin_memory()
-            self._blob = torch.empty(cap, dtype=torch.uint8, device=self.device)
-        return self._pinned, self._blob
+            sl["pinned"] = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            sl["blob"] = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        return sl
 
     def describe(self, shapes):
         """int64 [n, 8] descriptor table of `mic_resize_crop_u8` for images of the given (H, W)."""
@@ -83,9 +91,8 @@ class BatchTransform:
                 raise ValueError(f"expected uint8 [3, H, W] images (read_image(..., RGB)), got {a.dtype} {a.shape}")
             arrs.append(np.ascontiguousarray(a))
         desc, total = self.describe([a.shape[1:] for a in arrs])
-        if self._done is not None:
-            self._done.synchronize()
-        pinned, blob = self._stage(total + 8 * desc.size)
+        sl = self._stage(total + 8 + 8 * desc.size)
+        pinned, blob = sl["pinned"], sl["blob"]
         pv = pinned.numpy()
 
         def pack(k):
@@ -96,16 +103,25 @@ class BatchTransform:
         doff = (total + 7) // 8 * 8                                  # descriptor table rides in the same transfer
         pv[doff:doff + desc.nbytes] = desc.view(np.uint8).reshape(-1)
         nbytes = doff + desc.nbytes
-        blob[:nbytes].copy_(pinned[:nbytes], non_blocking=True)
-        self._done = torch.cuda.Event()
-        self._done.record()
+        cur = torch.cuda.current_stream(self.device)
+        cs = self._copy_stream
+        if sl["consumed"] is not None:
+            cs.wait_event(sl["consumed"])       # the kernel that read this device blob two batches ago is done
+        with torch.cuda.stream(cs):
+            blob[:nbytes].copy_(pinned[:nbytes], non_blocking=True)
+            sl["copied"] = torch.cuda.Event()
+            sl["copied"].record(cs)
+        cur.wait_event(sl["copied"])
         S = self.size
         shape = (n, 3, S, S) if self.channel_first else (n, S, S, 3)
         if out is None:
             out = torch.empty(shape, dtype=torch.uint8, device=self.device)
         assert tuple(out.shape) == shape and out.dtype == torch.uint8
         ops.resize_crop_u8(blob, blob[doff:nbytes].view(torch.int64).view(n, 8), n, S, out, self.channel_first)
+        sl["consumed"] = torch.cuda.Event()
+        sl["consumed"].record(cur)
         self.last_h2d_bytes = nbytes
+        self.last_blob, self.last_desc = blob, blob[doff:nbytes].view(torch.int64).view(n, 8)      # (bench: kernel-only timing)
         return out
 
 
