@@ -282,6 +282,40 @@ def test_attention_fwd_bwd(Tq, Tk, causal, masked, impl):
         ops.attention_impl(0)
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,causal", [(256, 12, 197, 197, False), (256, 16, 64, 64, True), (256, 16, 64, 50, False)])
+def test_attention_full_size_matches_torch(B, H, Tq, Tk, causal):
+    """BASELINE-size launches (3072 / 4096 (batch, head) pairs: every CTA slot of the grid is exercised) against torch's
+    fp32 attention on the same bf16 inputs; forward and all three gradients, relative RMS error."""
+    hd, d = 64, H * 64
+    g = torch.Generator().manual_seed(7)
+    q = (torch.randn(B * Tq, d, generator=g) * 1.2).to(BF16).to(DEV)
+    kv = (torch.randn(B * Tk, 2 * d, generator=g) * 1.2).to(BF16).to(DEV)
+    do = torch.randn(B * Tq, d, generator=g).to(BF16).to(DEV)
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, Tq, device=DEV)
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    scale = 1 / math.sqrt(hd)
+    ops.attention_fwd(q, kv[:, :d], kv[:, d:], out, lse, None, causal, B, H, Tq, Tk, scale)
+    ops.attention_bwd(q, kv[:, :d], kv[:, d:], out, do, lse, None, causal, dq, dkv[:, :d], dkv[:, d:], B, H, Tq, Tk, scale)
+    qf = q.float().view(B, Tq, H, hd).transpose(1, 2).requires_grad_(True)          # [B,H,T,hd]
+    kf = kv[:, :d].float().reshape(B, Tk, H, hd).transpose(1, 2).requires_grad_(True)
+    vf = kv[:, d:].float().reshape(B, Tk, H, hd).transpose(1, 2).requires_grad_(True)
+    want = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, is_causal=causal, scale=scale)
+    want.backward(do.float().view(B, Tq, H, hd).transpose(1, 2))
+    torch.cuda.synchronize()
+
+    def rms(a, b):
+        return float((a.float() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
+    assert rms(out.view(B, Tq, H, hd).transpose(1, 2), want.detach()) < 4e-3
+    assert rms(dq.view(B, Tq, H, hd).transpose(1, 2), qf.grad) < 8e-3
+    assert rms(dkv[:, :d].reshape(B, Tk, H, hd).transpose(1, 2), kf.grad) < 8e-3
+    assert rms(dkv[:, d:].reshape(B, Tk, H, hd).transpose(1, 2), vf.grad) < 8e-3
+    want_lse = torch.logsumexp(torch.einsum("bhqd,bhkd->bhqk", qf.detach() * scale, kf.detach()).masked_fill(
+        ~torch.tril(torch.ones(Tq, Tk, dtype=torch.bool, device=DEV)) if causal else torch.zeros(Tq, Tk, dtype=torch.bool, device=DEV),
+        float("-inf")), -1)
+    assert float((lse - want_lse).abs().max()) < 1e-4
+
+
 def test_attention_fully_masked_rows_are_zero():
     """A query whose keys are all padded gets a zero output and zero gradients (softmax over nothing) in both kernels."""
     B, H, hd, T = 2, 2, 64, 48
