@@ -95,8 +95,10 @@ def main():
 
 
 def one_shape():
-    """ATTN_ONE=1: a few launches of the ViT shape only (what the ncu capture profiles)."""
-    B, H, T = 256, 12, 197
+    """ATTN_ONE=1: a few launches of one self-attention shape only (what the ncu capture profiles); ATTN_T=64 ATTN_H=16
+    ATTN_CAUSAL=1 selects the mBART decoder shape instead of ViT-B/16's 197 tokens."""
+    B, H, T = 256, int(os.environ.get("ATTN_H", "12")), int(os.environ.get("ATTN_T", "197"))
+    causal = os.environ.get("ATTN_CAUSAL") == "1"
     d = H * 64
     qkv = torch.randn(B * T, 3 * d, device=DEV).bfloat16()
     o = torch.empty(B * T, d, dtype=torch.bfloat16, device=DEV)
@@ -104,8 +106,8 @@ def one_shape():
     lse = torch.empty(B, H, T, device=DEV)
     dqkv = torch.empty_like(qkv)
     for _ in range(3):
-        ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, lse, None, False, B, H, T, T, 0.125)
-        ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, do, lse, None, False, dqkv[:, :d], dqkv[:, d:2 * d],
+        ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, lse, None, causal, B, H, T, T, 0.125)
+        ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, do, lse, None, causal, dqkv[:, :d], dqkv[:, d:2 * d],
                           dqkv[:, 2 * d:], B, H, T, T, 0.125)
     torch.cuda.synchronize()
 
