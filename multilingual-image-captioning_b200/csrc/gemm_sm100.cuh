@@ -137,8 +137,13 @@ struct EpiStoreT {
   static constexpr int NBUF = NBUF_;
   static constexpr int EW = EW_;
   typedef EpiStoreParams Params;
+  // The 16-warp policy (96 registers per thread) takes every 64-column group as two 32-column halves: with 64 live
+  // accumulators it spilled 592 B per thread in the GELU epilogue of the fc1 forward GEMMs (the GEMM class furthest from
+  // the roofline in profiles/r02_gemm_table.txt).  The launcher never sends a residual to this policy.
+  static constexpr bool HALF_GROUPS = (EW_ == 16 && !ACT_BWD && NBUF_ == 1);
   struct State {
-    uint4 res[8];   // this thread's 64 residual values of the group about to be processed (loaded ahead by group_pre)
+    uint4 res[8];        // this thread's 64 residual values of the group about to be processed (loaded ahead by group_pre)
+    uint32_t keep[16];   // HALF_GROUPS: the packed bf16 outputs of the first half, until the second half completes the row
   };
   __device__ static void kernel_begin(const Params&, State&) {}
   __device__ static void kernel_end(const Params&, State&, const Shape&, int, int) {}
@@ -195,6 +200,91 @@ struct EpiStoreT {
         reinterpret_cast<bf16*>(p.D)[(long long)row * p.ldd + c] = __float2bfloat16_rn(x);
       }
     }
+  }
+
+  // HALF_GROUPS form: v = 32 consecutive columns [col0, col0+32); the two halves of a 64-column group arrive back to
+  // back (first the even, then the odd multiple of 32) and share the 128-byte-per-row staging tile: the pre-activation
+  // copy is staged half by half and stored after the second, the activated halves meet in the staging tile through
+  // st.keep.  No residual here (see HALF_GROUPS).
+  template <int NC>
+  __device__ static void group_n(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+    static_assert(NC == 32, "half groups are 32 columns");
+    const int hf = (col0 >> 5) & 1;
+    const int gcol0 = col0 - hf * 32;
+    if (gcol0 >= s.N) return;                     // warp-uniform: the whole 64-column group is outside the matrix
+    if (!p.tma_ok) {
+      chunk_scalar(p, s, ctx.row, col0, v);
+      return;
+    }
+    const int lane = ctx.lane;
+    uint8_t* stg = ctx.stg;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = col0 + u * 8;
+      float4 b0 = make_float4(0, 0, 0, 0), b1 = b0;
+      if (p.bias && c < s.N) {
+        b0 = *reinterpret_cast<const float4*>(p.bias + c);
+        b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+      }
+      float* x = v + u * 8;
+      x[0] = x[0] * p.out_scale + b0.x; x[1] = x[1] * p.out_scale + b0.y;
+      x[2] = x[2] * p.out_scale + b0.z; x[3] = x[3] * p.out_scale + b0.w;
+      x[4] = x[4] * p.out_scale + b1.x; x[5] = x[5] * p.out_scale + b1.y;
+      x[6] = x[6] * p.out_scale + b1.z; x[7] = x[7] * p.out_scale + b1.w;
+    }
+    if (p.D2) {
+      if (hf == 0) stg_acquire<0>(lane);          // the previous store out of this tile has been read
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* x = v + u * 8;
+        *reinterpret_cast<uint4*>(stg_addr(stg, lane, hf * 4 + u)) =
+            make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      }
+      if (hf == 1) stg_store(ctx.tmap_d2, stg, lane, gcol0, ctx.row0, false);
+    }
+    if (p.act != MIC_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
+    }
+    if (p.drop.seed_ptr) {
+      const uint32_t seed = *p.drop.seed_ptr + p.drop.site;
+      const uint32_t base = ((uint32_t)ctx.row * (uint32_t)s.N + (uint32_t)col0) >> 1;   // N, col0 even on this path
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        bool k0, k1;
+        drop_keep2(base + j, seed, p.drop.thr16, &k0, &k1);
+        v[2 * j] = k0 ? v[2 * j] * p.drop.scale : 0.f;
+        v[2 * j + 1] = k1 ? v[2 * j + 1] * p.drop.scale : 0.f;
+      }
+    }
+    if (p.d_f32) {
+      // fp32 output: 32 columns are exactly one 128-byte staging row
+      stg_acquire<0>(lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* x = v + u * 4;
+        *reinterpret_cast<float4*>(stg_addr(stg, lane, u)) = make_float4(x[0], x[1], x[2], x[3]);
+      }
+      stg_store(ctx.tmap_d, stg, lane, col0, ctx.row0, p.accumulate != 0);
+      return;
+    }
+    if (hf == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) st.keep[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      return;
+    }
+    stg_acquire<0>(lane);                          // (the pre-activation store, if any, has been read)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<uint4*>(stg_addr(stg, lane, u)) =
+          make_uint4(st.keep[4 * u], st.keep[4 * u + 1], st.keep[4 * u + 2], st.keep[4 * u + 3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* x = v + u * 8;
+      *reinterpret_cast<uint4*>(stg_addr(stg, lane, 4 + u)) =
+          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    }
+    stg_store(ctx.tmap_d, stg, lane, gcol0, ctx.row0, false);
   }
 
   // v: 64 consecutive columns [col0, col0+64) of row ctx.row (fp32 accumulators)
@@ -595,33 +685,42 @@ struct EpiSearchT {
     }
   }
   __device__ static void tile_end(const Params&, State&, const Shape&, int, int, int, int) {}
+  // The kernel loop hands this policy HALF groups (32 accumulator columns at a time, HALF_GROUPS below): with 64 live
+  // accumulators next to the top-8 state the epilogue spilled ~70 values per group to local memory in its hot path
+  // (536 B of spill stores, LDL between the MUFU.EX2 of the exp-sum; the search GEMM ran 200 us against 137 us for the
+  // same operand stream with a plain store epilogue).
+  static constexpr bool HALF_GROUPS = true;
   __device__ static void group(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
+    group_n<64>(p, st, s, ctx, col0, v);
+  }
+  template <int NC>
+  __device__ static void group_n(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
     if (col0 >= s.N) return;
-    const bool full = col0 + 64 <= s.N;
+    const bool full = col0 + NC <= s.N;
     const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     if (full && (bias_vec || !p.bias)) {
       if (p.bias) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < NC / 4; ++u) {
           const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + u * 4);
           v[u * 4 + 0] += b.x; v[u * 4 + 1] += b.y; v[u * 4 + 2] += b.z; v[u * 4 + 3] += b.w;
         }
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
+      for (int j = 0; j < NC; ++j) {
         const int c = col0 + j;
         v[j] = (c < s.N) ? (p.bias ? v[j] + p.bias[c] : v[j]) : -INFINITY;
       }
     }
     const unsigned mrel = static_cast<unsigned>(p.mask_token - col0);
-    if (mrel < 64u) {
+    if (mrel < static_cast<unsigned>(NC)) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = (mrel == static_cast<unsigned>(j)) ? -INFINITY : v[j];
+      for (int j = 0; j < NC; ++j) v[j] = (mrel == static_cast<unsigned>(j)) ? -INFINITY : v[j];
     }
     if (p.upper_val) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j)
+      for (int j = 0; j < NC; ++j)
         if (!(v[j] < st.uv || (v[j] == st.uv && col0 + j > st.ui))) v[j] = -INFINITY;
     }
     if constexpr (kGumbel) {            // `_sample`: a separate instantiation, the search kernels carry none of this
@@ -629,13 +728,13 @@ struct EpiSearchT {
       const unsigned long long base = (unsigned long long)ctx.row * (unsigned long long)s.N + (unsigned long long)col0;
       if (ctx.row < s.M) {
 #pragma unroll 4
-        for (int j = 0; j < 64; ++j)
+        for (int j = 0; j < NC; ++j)
           if (col0 + j < s.N) v[j] += gumbel_at(p.gumbel_k0, p.gumbel_k1, base + j, total);
       }
     }
     float cmax = v[0];
 #pragma unroll
-    for (int j = 1; j < 64; ++j) cmax = fmaxf(cmax, v[j]);
+    for (int j = 1; j < NC; ++j) cmax = fmaxf(cmax, v[j]);
     if (__any_sync(0xffffffffu, cmax > st.tv[SEARCH_TOPK - 1])) {
       // Each lane owns a row, so a per-value `if (v[j] > threshold) insert` makes the WARP run the ~40-instruction
       // sorted insert whenever ANY of its 32 rows has a hit: ~60 % of the columns although a lane itself inserts
@@ -648,7 +747,7 @@ struct EpiSearchT {
       float2* q = reinterpret_cast<float2*>(ctx.stg);          // [QCAP][32 lanes] (value, column bits)
       int cnt = 0;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
+      for (int j = 0; j < NC; ++j) {
         if (v[j] > thr) {
           if (cnt < QCAP) q[cnt * 32 + ctx.lane] = make_float2(v[j], __int_as_float(col0 + j));
           ++cnt;
@@ -659,7 +758,7 @@ struct EpiSearchT {
         // sequential scan, FULLY unrolled - a partially unrolled scan indexes v[] dynamically, which puts the
         // whole 64-float group into local memory
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
+        for (int j = 0; j < NC; ++j) {
           if (v[j] > st.tv[SEARCH_TOPK - 1]) {
             float cv = v[j];
             int ci = col0 + j;
@@ -706,7 +805,7 @@ struct EpiSearchT {
     const float nm2 = nm * MIC_LOG2E;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc += ex2_approx(fmaf(v[j], MIC_LOG2E, -nm2));
+    for (int j = 0; j < NC; ++j) acc += ex2_approx(fmaf(v[j], MIC_LOG2E, -nm2));
     st.sm = st.sm * ex2_approx((st.mx - nm) * MIC_LOG2E) + acc;
     st.mx = nm;
   }
@@ -743,6 +842,11 @@ template <class E, class = void>
 struct EpiHasPrefetch { static constexpr bool value = false; };
 template <class E>
 struct EpiHasPrefetch<E, decltype((void)&E::tile_prefetch)> { static constexpr bool value = true; };
+
+template <class E, class = void>
+struct EpiHalfGroups { static constexpr bool value = false; };
+template <class E>
+struct EpiHalfGroups<E, decltype((void)E::HALF_GROUPS)> { static constexpr bool value = E::HALF_GROUPS; };
 
 template <int A_MN, int B_MN, int BN, class Epi>
 __global__ void __launch_bounds__(128 + Epi::EW * 32, 1)
@@ -920,6 +1024,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int g = g_begin; g < g_end; ++g) {
+        if constexpr (EpiHalfGroups<Epi>::value) {
+          // register-heavy reduction epilogues take the group as two 32-column halves (32 live accumulators each)
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            float v[GROUP_COLS / 2];
+            tmem_ld_32x32(taddr + g * GROUP_COLS + hf * 32, v);
+            tmem_ld_wait();
+            if (g == g_end - 1 && hf == 1) {         // accumulator drained: hand the TMEM buffer back early
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            }
+            Epi::template group_n<GROUP_COLS / 2>(ep, st, shape, ctx, tc.n_blk * BN + g * GROUP_COLS + hf * 32, v);
+          }
+          continue;
+        }
         float v[GROUP_COLS];
         tmem_ld_32x32(taddr + g * GROUP_COLS, v);
         tmem_ld_32x32(taddr + g * GROUP_COLS + 32, v + 32);

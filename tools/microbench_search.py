@@ -37,3 +37,19 @@ print(f"search (TMA boxes) : {timeit(lambda: ops.lm_head_search(h, E, bias, -1, 
 print(f"search (packed)    : {timeit(lambda: ops.lm_head_search_packed(ht, et, bias, -1, R, V, d, ws)):8.1f} us")
 print(f"merge              : {timeit(lambda: ops.search_merge(ws, R)):8.1f} us")
 print(f"pack embedding     : {timeit(lambda: ops.pack_kmajor_tiles(E, 256, et), 5):8.1f} us")
+# ---- what bounds it?  Same operand stream with (a) half the rows (one m-tile: every weight tile is used once), (b) a plain
+# bf16-store epilogue instead of the search epilogue, (c) R = 128 with the search epilogue
+Vp = 250048
+for rows in (256, 128):
+    hh = h[:rows].contiguous()
+    out = torch.empty(rows, Vp, dtype=bf, device=dev)
+    t = timeit(lambda: ops.gemm(hh, E[:Vp], out=out, block_n=256))
+    print(f"plain GEMM [{rows} x {Vp} x {d}] bf16 store : {t:8.1f} us  ({2.0 * rows * Vp * d / t / 1e6:6.0f} TFLOP/s, {Vp * d * 2 / t / 1e3:6.0f} GB/s of weights)")
+n128 = ops.lm_head_search_num_partials(128)
+ws128 = {"nparts": n128, "pmax": torch.empty(n128, 128, device=dev), "psum": torch.empty(n128, 128, device=dev),
+         "cand_val": torch.empty(n128, 128, 8, device=dev), "cand_idx": torch.empty(n128, 128, 8, device=dev, dtype=torch.int32),
+         "row_lp": torch.empty(128, 8, device=dev), "row_tok": torch.empty(128, 8, device=dev, dtype=torch.int32),
+         "row_ml": torch.empty(128, 2, device=dev)}
+h128 = h[:128].contiguous()
+t = timeit(lambda: ops.lm_head_search(h128, E, bias, -1, ws128))
+print(f"search (TMA boxes), 128 rows        : {t:8.1f} us  ({V * d * 2 / t / 1e3:6.0f} GB/s of weights)")
