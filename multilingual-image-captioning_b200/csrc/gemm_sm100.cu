@@ -257,7 +257,7 @@ extern "C" int mic_gemm_bf16(void* stream, int a_mn_major, int b_mn_major, const
   // 16 epilogue warps (one 64-column group per warp and tile) for the activation epilogues (issue bound); tried for the
   // residual + dropout epilogues of the short-K GEMMs as well: no gain (profiles/r02_gemm_epilogue_costs.txt)
   if (!a_mn_major && b_mn_major && act != MIC_ACT_NONE && tma && o.bn == 256 && !residual)
-    return launch_one<0, 1, 256, EpiStoreAct16>(s, o, ep);       // (its half-group epilogue carries no residual path)
+    return launch_one<0, 1, 256, EpiStoreAct16>(s, o, ep);       // (its epilogue carries no residual path)
   if (!a_mn_major && b_mn_major) return launch_bn<0, 1, EpiStore>(s, o, ep);
   if (!a_mn_major && !b_mn_major) return launch_bn<0, 0, EpiStore>(s, o, ep);
   if (a_mn_major && b_mn_major) return launch_bn<1, 1, EpiStore>(s, o, ep);

@@ -137,10 +137,11 @@ struct EpiStoreT {
   static constexpr int NBUF = NBUF_;
   static constexpr int EW = EW_;
   typedef EpiStoreParams Params;
-  // The 16-warp policy (96 registers per thread) takes every 64-column group as two 32-column halves: with 64 live
-  // accumulators it spilled 592 B per thread in the GELU epilogue of the fc1 forward GEMMs (the GEMM class furthest from
-  // the roofline in profiles/r02_gemm_table.txt).  The launcher never sends a residual to this policy.
-  static constexpr bool HALF_GROUPS = (EW_ == 16 && !ACT_BWD && NBUF_ == 1);
+  // The single-buffer store policies take every 64-column group as two 32-column halves: with 64 live accumulators the
+  // 16-warp form (96 registers per thread) spilled 592 B per thread in the GELU epilogue of the fc1 forward GEMMs (the GEMM
+  // class furthest from the roofline in profiles/r02_gemm_table.txt) and the 8-warp form 76 B next to its residual registers.
+  // The 16-warp form carries no residual path (the launcher routes residual epilogues to the 8-warp policy).
+  static constexpr bool HALF_GROUPS = (!ACT_BWD && NBUF_ == 1);
   struct State {
     uint4 res[8];        // this thread's 64 residual values of the group about to be processed (loaded ahead by group_pre)
     uint32_t keep[16];   // HALF_GROUPS: the packed bf16 outputs of the first half, until the second half completes the row
@@ -165,7 +166,7 @@ struct EpiStoreT {
   // pulled into L2 one tile earlier by tile_prefetch.  Safe for in-place use (residual == D): a thread reads exactly
   // the elements it later overwrites.
   __device__ static void group_pre(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0) {
-    if (!p.residual || !p.tma_ok) return;
+    if (EW_ == 16 || !p.residual || !p.tma_ok) return;
     const bool row_ok = ctx.row < s.M;
     const bf16* r = p.residual + (long long)ctx.row * p.ldr + col0;
 #pragma unroll
@@ -205,7 +206,7 @@ struct EpiStoreT {
   // HALF_GROUPS form: v = 32 consecutive columns [col0, col0+32); the two halves of a 64-column group arrive back to
   // back (first the even, then the odd multiple of 32) and share the 128-byte-per-row staging tile: the pre-activation
   // copy is staged half by half and stored after the second, the activated halves meet in the staging tile through
-  // st.keep.  No residual here (see HALF_GROUPS).
+  // st.keep.  The residual registers of the whole group were loaded ahead by group_pre; half hf consumes res[4 hf .. 4 hf + 3].
   template <int NC>
   __device__ static void group_n(const Params& p, State& st, const Shape& s, const EpiCtx& ctx, int col0, float* v) {
     static_assert(NC == 32, "half groups are 32 columns");
@@ -256,6 +257,20 @@ struct EpiStoreT {
         v[2 * j] = k0 ? v[2 * j] * p.drop.scale : 0.f;
         v[2 * j + 1] = k1 ? v[2 * j + 1] * p.drop.scale : 0.f;
       }
+    }
+    if (EW_ != 16 && p.residual) {      // (the 96-register 16-warp form has no room for the residual registers)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float* x = v + u * 8;
+        const uint4 r = hf ? st.res[4 + u] : st.res[u];
+        float2 f;
+        f = unpack_bf16(r.x); x[0] += f.x; x[1] += f.y;
+        f = unpack_bf16(r.y); x[2] += f.x; x[3] += f.y;
+        f = unpack_bf16(r.z); x[4] += f.x; x[5] += f.y;
+        f = unpack_bf16(r.w); x[6] += f.x; x[7] += f.y;
+      }
+      // the next group's residual loads go out as soon as this group's registers are free (overlaps the staging below)
+      if (hf == 1 && ctx.next_col >= 0) group_pre(p, st, s, ctx, ctx.next_col);
     }
     if (p.d_f32) {
       // fp32 output: 32 columns are exactly one 128-byte staging row
@@ -1025,7 +1040,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll 1
       for (int g = g_begin; g < g_end; ++g) {
         if constexpr (EpiHalfGroups<Epi>::value) {
-          // register-heavy reduction epilogues take the group as two 32-column halves (32 live accumulators each)
+          // register-heavy epilogues take the group as two 32-column halves (32 live accumulators each)
+          ctx.next_col = g + 1 < g_end ? tc.n_blk * BN + (g + 1) * GROUP_COLS : -1;
 #pragma unroll 1
           for (int hf = 0; hf < 2; ++hf) {
             float v[GROUP_COLS / 2];
