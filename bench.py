@@ -263,10 +263,14 @@ def run_ours(args):
     ops.TIMED_FLOPS.clear()
     model.engine.overlap_wgrad = True
     # ---- timed region 2: end to end through the public API with host buffers ----
+    # (two untimed steps first: the host path allocates its two device landing buffers and the copy stream on first use)
+    pinned_loss = torch.zeros(1).pin_memory()
+    for _ in range(2):
+        mic_b200.train_step(state, host)
+    barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     lossv = 0.0
-    pinned_loss = torch.zeros(1).pin_memory()
     prev = None
     for i in range(args.steps):
         # pinned host -> device copy of THIS step's inputs (copy stream, overlaps the previous step's GPU work)
