@@ -274,6 +274,7 @@ struct EpiStoreT {
     }
     if (p.d_f32) {
       // fp32 output: 32 columns are exactly one 128-byte staging row
+      if (col0 >= s.N) return;                     // warp-uniform: this half lies wholly outside the matrix
       stg_acquire<0>(lane);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
