@@ -12,8 +12,10 @@
 // Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 spare,
 // w4..w11 epilogue.  An epilogue warp owns one TMEM lane quarter (32 rows) and a share of the tile's
 // 64-column groups.  Outputs leave through a warp-private 4 KB swizzled staging buffer and TMA bulk
-// stores (coalesced, asynchronous, tails clipped by the tensor map); residual tiles enter through the
-// same buffer with coalesced 16-byte loads.
+// stores (coalesced, asynchronous, tails clipped by the tensor map).  Register-heavy policies (store,
+// search) take a group as two 32-column halves (HALF_GROUPS: 32 live accumulators instead of 64 - the
+// 64-column form spilled to local memory in the hot path); residual rows are L2-prefetched one tile
+// ahead and loaded into registers before the accumulator wait (tile_prefetch / group_pre).
 #pragma once
 
 #include "common.cuh"
